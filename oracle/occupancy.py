@@ -1,0 +1,610 @@
+"""CPU oracle for the occupancy log-density + gradient hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``biolith_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` do, and only as the checker / the
+timed CPU baseline, never as the product path.
+
+PARITY STATUS: **unpinned against numpyro**.  The reference (timmh/biolith) only
+*declares* the probabilistic program; the arithmetic of the path (enumeration
+sum-product, clamped Bernoulli / Poisson / Categorical log-probs, MaskedDistribution,
+reverse-mode AD) lives in numpyro>=0.18 / funsor>=0.4.5 / jax>=0.5 (lower bounds in
+/root/reference/pyproject.toml:22-28, no lock file), none of which is installed or
+installable here.  This file therefore restates (1) the reference's own model bodies
+operation by operation and (2) the *published* numpyro semantics for the distributions
+they call.  It is pinned three ways instead:
+  * the data side is pinned to the reference's own ``simulate*()`` generators
+    (tests/golden/*.npz, produced by tests/golden/make_golden.py importing
+    /root/reference with jax/numpyro stubbed);
+  * the op-by-op "enumerated" restatement and the closed-form restatement are
+    independent derivations and must agree to ~1e-12;
+  * closed-form gradients are checked against central finite differences of the
+    enumerated restatement.
+
+Two independent restatements are provided per model:
+
+``*_log_joint_enumerated``  follows the reference model body line by line,
+    materialising the enumerated tensor ``(|enum|, J, P, S, Sp)`` exactly as
+    numpyro + funsor would, then summing / logsumexp-ing it.  No gradient.
+``*_logp_grad``             closed-form per-site log-marginal and hand-derived
+    reverse-mode gradient; this is the algorithm the CUDA kernels implement.
+
+Reference lines restated (paths relative to /root/reference):
+  biolith/models/occu.py:135-242      (occu body)
+  biolith/models/occu_rn.py:123-222   (occu_rn body)
+  biolith/models/occu_cop.py:146-255  (occu_cop body)
+  biolith/regression/linear.py:16-66  (LinearRegression)
+  biolith/utils/modeling.py:8-39      (mask_missing_obs / flatten / reshape)
+  biolith/utils/distributions.py:6-40 (RightTruncatedPoisson)
+  biolith/utils/data.py:113-140       (period-dim insertion, fp32 cast)
+
+numpyro semantics restated (numpyro/distributions/{discrete,util,distribution}.py,
+numpyro>=0.18; recalled, not vendored):
+  clamp_probs(p)            = clip(p, finfo.tiny, 1 - finfo.eps)
+  BernoulliProbs.log_prob   = xlogy(v, p~) + xlog1py(1 - v, -p~)
+  Poisson.log_prob          = xlogy(v, rate) - gammaln(v + 1) - rate
+  CategoricalLogits         = logits - logsumexp(logits)   (normalised)
+  MaskedDistribution        = where(m, base.log_prob(where(m, v, feasible)), 0)
+  Beta / Exponential priors are sampled in unconstrained space through
+  SigmoidTransform / ExpTransform with their log-Jacobians (potential_fn).
+
+Parameter vector layout used everywhere in this repo (one chain):
+  theta = [ beta (Kb = Ks+1) | alpha (Ka = Ko+1) | extras ]
+  extras (unconstrained), in this order when enabled:
+     occu     : logit(prob_fp_constant), logit(prob_fp_unoccupied)
+     occu_rn  : logit(prob_fp_constant)
+     occu_cop : log(rate_fp_constant), log(rate_fp_unoccupied)
+Only n_species == 1 is restated in closed form (the enumerated form handles Sp >= 1).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+from scipy.special import expit, gammaln, xlog1py, xlogy
+
+LOG_2PI = float(np.log(2.0 * np.pi))
+
+
+def logsumexp(a, axis=None, keepdims=False):
+    """Max-shifted log-sum-exp (jax.scipy.special.logsumexp semantics for finite maxima)."""
+    a = np.asarray(a, np.float64)
+    amax = np.max(a, axis=axis, keepdims=True)
+    amax = np.where(np.isfinite(amax), amax, 0.0)
+    with np.errstate(divide="ignore"):
+        out = np.log(np.sum(np.exp(a - amax), axis=axis, keepdims=True)) + amax
+    return out if keepdims else np.squeeze(out, axis=axis)
+
+
+# --------------------------------------------------------------------------- data
+@dataclass
+class Prepared:
+    """Output of the reference's NaN-mask resolution (occu.py:136-142)."""
+
+    y: np.ndarray  # (Sp, S, P, J) float64, NaN where masked by covariates or missing
+    X: np.ndarray  # (S, Ks) NaN -> 0
+    W: np.ndarray  # (S, P, J, Ko) NaN -> 0
+    T: np.ndarray  # (S, P, J) session duration (ones if absent)
+    mask: np.ndarray  # (Sp, S, P, J) bool == isfinite(y)  (modeling.py:15-17)
+
+
+def ensure_period_dim(site_covs, obs_covs, obs, session_duration=None):
+    """biolith/utils/data.py:113-127 (_ensure_season_dim)."""
+    if obs_covs is not None:
+        if obs_covs.ndim == 2:
+            obs_covs = obs_covs[:, :, None]
+        if obs_covs.ndim == 3:
+            obs_covs = obs_covs[:, None, :, :]
+    if obs is not None and obs.ndim == 2:
+        obs = obs[:, None, :]
+    if session_duration is not None and session_duration.ndim == 2:
+        session_duration = session_duration[:, None, :]
+    return site_covs, obs_covs, obs, session_duration
+
+
+def prepare(site_covs, obs_covs, obs, session_duration=None, dtype=np.float32) -> Prepared:
+    """NaN-mask resolution, occu.py:136-142 == occu_rn.py:124-130 == occu_cop.py:151-157.
+
+    ``dtype`` is the dtype the reference would hold the arrays in (fp32 unless
+    jax_enable_x64; data.py:135-140) -- it only matters for nan_to_num's +-inf
+    replacement values.  Arithmetic afterwards is float64.
+    """
+    site_covs = np.asarray(site_covs, dtype=dtype)
+    obs_covs = np.asarray(obs_covs, dtype=dtype)
+    obs = np.asarray(obs, dtype=dtype)
+    assert obs.ndim == 4 and site_covs.ndim == 2 and obs_covs.ndim == 4
+    S, P, J, _ = obs_covs.shape
+    assert obs.shape[1:] == (S, P, J) and site_covs.shape[0] == S
+    obs_mask = np.isnan(obs_covs).any(axis=-1) | np.isnan(site_covs).any(axis=-1)[:, None, None]
+    obs = np.where(obs_mask[None, ...], np.nan, obs)
+    obs_covs = np.nan_to_num(obs_covs)
+    site_covs = np.nan_to_num(site_covs)
+    if session_duration is None:
+        T = np.ones((S, P, J), dtype=np.float64)  # occu_cop.py:146-148
+    else:
+        T = np.asarray(session_duration, dtype=np.float64)
+    return Prepared(
+        y=obs.astype(np.float64),
+        X=site_covs.astype(np.float64),
+        W=obs_covs.astype(np.float64),
+        T=T,
+        mask=np.isfinite(obs),
+    )
+
+
+def n_extras(model: str, fp_constant=False, fp_unoccupied=False) -> int:
+    if model == "occu_rn":
+        assert not fp_unoccupied
+    return int(bool(fp_constant)) + int(bool(fp_unoccupied))
+
+
+def split_theta(theta, Ks, Ko, fp_constant, fp_unoccupied):
+    theta = np.asarray(theta, dtype=np.float64)
+    Kb, Ka = Ks + 1, Ko + 1
+    beta = theta[:Kb]
+    alpha = theta[Kb : Kb + Ka]
+    i = Kb + Ka
+    xc = xu = None
+    if fp_constant:
+        xc = theta[i]
+        i += 1
+    if fp_unoccupied:
+        xu = theta[i]
+        i += 1
+    assert i == theta.shape[0], "theta has wrong length"
+    return beta, alpha, xc, xu
+
+
+# ---------------------------------------------------------------- numpyro pieces
+def _finfo(dtype):
+    return np.finfo(np.dtype(dtype))
+
+
+def clamp_probs(p, finfo):
+    return np.clip(p, finfo.tiny, 1.0 - finfo.eps)
+
+
+def bernoulli_log_prob(p, v, finfo):
+    pt = clamp_probs(p, finfo)
+    return xlogy(v, pt) + xlog1py(1.0 - v, -pt)
+
+
+def poisson_log_prob(rate, v):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return xlogy(v, rate) - gammaln(v + 1.0) - rate
+
+
+def normal_log_prob(x, loc=0.0, scale=1.0):
+    return -0.5 * ((x - loc) / scale) ** 2 - np.log(scale) - 0.5 * LOG_2PI
+
+
+def _linear(coef, covs_flat):
+    """LinearRegression.__call__, linear.py:48-66.  coef (Sp, k+1), covs (n, k) -> (n, Sp)."""
+    intercept = coef[..., 0]
+    slopes = coef[..., 1:]
+    linear = np.tensordot(slopes, covs_flat, axes=([-1], [1]))  # (Sp, n)
+    return linear.T + intercept.reshape((1,) + intercept.shape)
+
+
+def _flatten(covs):
+    """modeling.py:22-28: (n_covs, *obs_shape) -> (n_obs, n_covs), obs_shape."""
+    return covs.reshape(covs.shape[0], -1).T, covs.shape[1:]
+
+
+def _extras_prior_sigmoid(x, a=2.0, b=5.0):
+    """Beta(a,b) on c = sigmoid(x), plus log|dc/dx| (SigmoidTransform)."""
+    c = expit(x)
+    logc = -np.logaddexp(0.0, -x)
+    log1mc = -np.logaddexp(0.0, x)
+    lp = (a - 1.0) * logc + (b - 1.0) * log1mc + gammaln(a + b) - gammaln(a) - gammaln(b)
+    return c, lp + logc + log1mc, a * (1.0 - c) - b * c  # value, log-density, d/dx
+
+
+def _extras_prior_exp(x, rate=1.0):
+    """Exponential(rate) on c = exp(x), plus log|dc/dx| = x (ExpTransform)."""
+    c = np.exp(x)
+    return c, np.log(rate) - rate * c + x, -rate * c + 1.0
+
+
+# ===================================================================== enumerated
+def occu_log_joint_enumerated(
+    theta, site_covs, obs_covs, obs, *, false_positives_constant=False,
+    false_positives_unoccupied=False, dtype=np.float32, prior=True,
+):
+    """occu.py:135-242 op by op; theta = [beta(Sp*Kb) | alpha(Sp*Ka) | extras]."""
+    finfo = _finfo(dtype)
+    pr = prepare(site_covs, obs_covs, obs, dtype=dtype)
+    Sp, S, P, J = pr.y.shape
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    theta = np.asarray(theta, np.float64)
+    nb, na = Sp * (Ks + 1), Sp * (Ko + 1)
+    beta = theta[:nb].reshape(Sp, Ks + 1)
+    alpha = theta[nb : nb + na].reshape(Sp, Ko + 1)
+    rest = list(theta[nb + na :])
+    lp = 0.0
+    c = u = 0.0
+    if false_positives_constant:  # occu.py:146-150, Beta(2,5) in logit space
+        c, l, _ = _extras_prior_sigmoid(rest.pop(0))
+        lp += l if prior else 0.0
+    if false_positives_unoccupied:  # occu.py:153-157
+        u, l, _ = _extras_prior_sigmoid(rest.pop(0))
+        lp += l if prior else 0.0
+    assert not rest
+    if prior:  # linear.py:28, prior.expand([k+1]).to_event(1), default Normal(0,1)
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+    # occu.py:176-180
+    site_flat, site_shape = _flatten(pr.X.transpose(1, 0))
+    obs_flat, obs_shape = _flatten(pr.W.transpose(3, 2, 1, 0))
+    y = pr.y.transpose(3, 2, 1, 0)  # (J,P,S,Sp)
+    m = np.isfinite(y)
+    occ_linear = _linear(beta, site_flat).reshape(site_shape + (Sp,))  # (S,Sp)
+    psi = expit(occ_linear)  # occu.py:207 -> broadcast (P,S,Sp)
+    psi = np.broadcast_to(psi, (P, S, Sp))
+    z = np.array([0.0, 1.0]).reshape(2, 1, 1, 1, 1)  # enum dim = -5
+    log_pz = bernoulli_log_prob(psi, z, finfo)  # (2,1,P,S,Sp)
+    p = expit(_linear(alpha, obs_flat).reshape(obs_shape + (Sp,)))  # (J,P,S,Sp)
+    p_fp = 1 - (1 - z * p) * (1 - c) * (1 - (1 - z) * u)  # occu.py:229-235
+    v = np.where(m, y, 0.0)
+    ll = np.where(m, bernoulli_log_prob(p_fp, v, finfo), 0.0)  # (2,J,P,S,Sp)
+    site_ll = ll.sum(axis=1, keepdims=True) + log_pz  # (2,1,P,S,Sp)
+    return float(lp + logsumexp(site_ll, axis=0).sum())
+
+
+def occu_rn_log_joint_enumerated(
+    theta, site_covs, obs_covs, obs, *, max_abundance=100, false_positives_constant=False,
+    dtype=np.float32, prior=True,
+):
+    """occu_rn.py:123-222 op by op."""
+    finfo = _finfo(dtype)
+    pr = prepare(site_covs, obs_covs, obs, dtype=dtype)
+    Sp, S, P, J = pr.y.shape
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    theta = np.asarray(theta, np.float64)
+    nb, na = Sp * (Ks + 1), Sp * (Ko + 1)
+    beta = theta[:nb].reshape(Sp, Ks + 1)
+    alpha = theta[nb : nb + na].reshape(Sp, Ko + 1)
+    rest = list(theta[nb + na :])
+    lp = 0.0
+    c = 0.0
+    if false_positives_constant:
+        c, l, _ = _extras_prior_sigmoid(rest.pop(0))
+        lp += l if prior else 0.0
+    assert not rest
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+    site_flat, site_shape = _flatten(pr.X.transpose(1, 0))
+    obs_flat, obs_shape = _flatten(pr.W.transpose(3, 2, 1, 0))
+    y = pr.y.transpose(3, 2, 1, 0)
+    m = np.isfinite(y)
+    abu_linear = _linear(beta, site_flat).reshape(site_shape + (Sp,))
+    abundance = np.broadcast_to(np.exp(abu_linear), (P, S, Sp))  # occu_rn.py:188
+    # distributions.py:31-40: Categorical(logits=Poisson(rate[...,None]).log_prob(0..K))
+    support = np.arange(max_abundance + 1, dtype=np.float64)
+    logits = poisson_log_prob(abundance[..., None], support)  # (P,S,Sp,K+1)
+    log_pN = logits - logsumexp(logits, axis=-1, keepdims=True)
+    log_pN = np.moveaxis(log_pN, -1, 0)[:, None]  # (K+1,1,P,S,Sp)
+    N = support.reshape(-1, 1, 1, 1, 1)
+    r = expit(_linear(alpha, obs_flat).reshape(obs_shape + (Sp,)))  # (J,P,S,Sp)
+    p_it = 1.0 - (1.0 - r) ** N  # occu_rn.py:213 -> (K+1,J,P,S,Sp)
+    v = np.where(m, y, 0.0)
+    ll = np.where(m, bernoulli_log_prob(1 - (1 - p_it) * (1 - c), v, finfo), 0.0)
+    site_ll = ll.sum(axis=1, keepdims=True) + log_pN
+    return float(lp + logsumexp(site_ll, axis=0).sum())
+
+
+def occu_cop_log_joint_enumerated(
+    theta, site_covs, obs_covs, obs, session_duration=None, *, false_positives_constant=False,
+    false_positives_unoccupied=False, dtype=np.float32, prior=True,
+):
+    """occu_cop.py:146-255 op by op."""
+    finfo = _finfo(dtype)
+    pr = prepare(site_covs, obs_covs, obs, session_duration, dtype=dtype)
+    Sp, S, P, J = pr.y.shape
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    theta = np.asarray(theta, np.float64)
+    nb, na = Sp * (Ks + 1), Sp * (Ko + 1)
+    beta = theta[:nb].reshape(Sp, Ks + 1)
+    alpha = theta[nb : nb + na].reshape(Sp, Ko + 1)
+    rest = list(theta[nb + na :])
+    lp = 0.0
+    c = u = 0.0
+    if false_positives_constant:  # occu_cop.py:160-164, Exponential(1) in log space
+        c, l, _ = _extras_prior_exp(rest.pop(0))
+        lp += l if prior else 0.0
+    if false_positives_unoccupied:  # occu_cop.py:167-171
+        u, l, _ = _extras_prior_exp(rest.pop(0))
+        lp += l if prior else 0.0
+    assert not rest
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+    site_flat, site_shape = _flatten(pr.X.transpose(1, 0))
+    obs_flat, obs_shape = _flatten(pr.W.transpose(3, 2, 1, 0))
+    T = pr.T.transpose(2, 1, 0)[..., None]  # occu_cop.py:192 -> (J,P,S,1)
+    y = pr.y.transpose(3, 2, 1, 0)
+    m = np.isfinite(y)
+    psi = np.broadcast_to(expit(_linear(beta, site_flat).reshape(site_shape + (Sp,))), (P, S, Sp))
+    z = np.array([0.0, 1.0]).reshape(2, 1, 1, 1, 1)
+    log_pz = bernoulli_log_prob(psi, z, finfo)
+    rate = np.exp(_linear(alpha, obs_flat).reshape(obs_shape + (Sp,)))
+    l_det = z * rate + (1 - z) * u + c  # occu_cop.py:243-247
+    v = np.where(m, y, 0.0)
+    ll = np.where(m, poisson_log_prob(T * l_det, v), 0.0)
+    site_ll = ll.sum(axis=1, keepdims=True) + log_pz
+    return float(lp + logsumexp(site_ll, axis=0).sum())
+
+
+# ==================================================================== closed form
+def _softplus(x):
+    return np.logaddexp(0.0, x)
+
+
+def _clamped_log_sigmoid_pair(x, finfo):
+    """log(p~), log1p(-p~), and the in-range indicator for p = sigmoid(x), p~ = clamp_probs(p).
+
+    Clamp decisions are taken in log space (exact): p < 1-eps <=> log(1-p) > log(eps) and
+    p > tiny <=> log(p) > log(tiny), so fp64 rounding of p near 1 cannot flip them.
+    """
+    p = expit(x)
+    lp = -_softplus(-x)
+    l1mp = -_softplus(x)
+    lo = lp <= np.log(finfo.tiny)
+    hi = l1mp <= np.log(finfo.eps)
+    inr = ~(lo | hi)
+    logp = np.where(inr, lp, np.where(lo, np.log(finfo.tiny), np.log1p(-finfo.eps)))
+    log1mp = np.where(inr, l1mp, np.where(lo, np.log1p(-finfo.tiny), np.log(finfo.eps)))
+    return p, logp, log1mp, inr
+
+
+def _bern_terms_from_log1mP(lq, y, m, finfo, dlq_dnu, dlq_dc):
+    """Clamped Bernoulli log-prob of y given P = 1 - exp(lq), and its derivatives through lq.
+
+    lq = log(1 - P) is exact (log space); P~ = clip(P, tiny, 1 - eps):
+      y = 0: log1p(-P~) = lq            if tiny < P < 1-eps  (<=> lq > log eps)
+      y = 1: log(P~)    = log(-expm1(lq))
+    d/dx = dt/dlq * dlq/dx with dt/dlq = 1 (y=0) or -(1-P)/P (y=1), zero where clipped.
+    """
+    P = -np.expm1(lq)
+    log_eps = np.log(finfo.eps)
+    inr = (lq > log_eps) & (P > finfo.tiny)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t_y0 = np.where(inr, lq, np.where(P <= finfo.tiny, np.log1p(-finfo.tiny), log_eps))
+        t_y1 = np.where(inr, np.log(np.where(inr, P, 1.0)),
+                        np.where(P <= finfo.tiny, np.log(finfo.tiny), np.log1p(-finfo.eps)))
+        dt_dlq = np.where(inr, np.where(y > 0.5, -np.exp(lq) / np.where(inr, P, 1.0), 1.0), 0.0)
+    t = np.where(m, np.where(y > 0.5, t_y1, t_y0), 0.0)
+    dt_dlq = np.where(m, dt_dlq, 0.0)
+    return t, dt_dlq * dlq_dnu, dt_dlq * dlq_dc
+
+
+def _units(pr: Prepared):
+    """Flatten (site, period) into independent units; species 0 only."""
+    Sp, S, P, J = pr.y.shape
+    assert Sp == 1, "closed form restated for n_species == 1"
+    U = S * P
+    X = np.repeat(pr.X, P, axis=0)  # unit u = s*P + p shares site s covariates
+    W = pr.W.reshape(U, J, -1)
+    T = pr.T.reshape(U, J)
+    m = pr.mask[0].reshape(U, J)
+    y = np.where(m, pr.y[0].reshape(U, J), 0.0)
+    return X, W, T, y, m
+
+
+def occu_logp_grad(
+    theta, pr: Prepared, *, fp_constant=False, fp_unoccupied=False, dtype=np.float32,
+    prior=True, return_site_terms=False,
+):
+    """Closed-form occu log-density + gradient.  theta: (D,)."""
+    finfo = _finfo(dtype)
+    X, W, T, y, m = _units(pr)
+    Ks, Ko = X.shape[1], W.shape[2]
+    beta, alpha, xc, xu = split_theta(theta, Ks, Ko, fp_constant, fp_unoccupied)
+    c = u = 0.0
+    lp = 0.0
+    gx = []
+    if fp_constant:
+        c, l, dc = _extras_prior_sigmoid(xc)
+        lp += l if prior else 0.0
+    if fp_unoccupied:
+        u, l, du = _extras_prior_sigmoid(xu)
+        lp += l if prior else 0.0
+    eta = beta[0] + X @ beta[1:]
+    nu = alpha[0] + W @ alpha[1:]  # (U,J)
+    psi, logpsi, log1mpsi, in_psi = _clamped_log_sigmoid_pair(eta, finfo)
+    if not (fp_constant or fp_unoccupied):
+        p, logp, log1mp, in_p = _clamped_log_sigmoid_pair(nu, finfo)
+        t1 = np.where(m, y * logp + (1 - y) * log1mp, 0.0)
+        dt1_dnu = np.where(m & in_p, y - p, 0.0)  # y(1-p) - (1-y)p
+        dt1_dc = 0.0
+        P0 = 0.0
+    else:
+        # "ideal arithmetic" form: log(1-P1) = log(1-p) + log(1-c) is carried in log space so
+        # that no 1-(1-x) cancellation enters (the reference's fp64 run has that noise; the
+        # clamp decisions are made on the exact quantities)
+        p = expit(nu)
+        lq = -_softplus(nu) + np.log1p(-c)
+        t1, dt1_dnu, dt1_dc = _bern_terms_from_log1mP(lq, y, m, finfo, dlq_dnu=-p, dlq_dc=-1.0 / (1.0 - c))
+        P0 = -np.expm1(np.log1p(-c) + np.log1p(-u))
+    n1 = (m * y).sum(axis=1)
+    n0 = (m * (1 - y)).sum(axis=1)
+    P0t = clamp_probs(P0, finfo)
+    in0 = (P0 > finfo.tiny) and (P0 < 1.0 - finfo.eps)
+    L0 = n1 * np.log(P0t) + n0 * np.log1p(-P0t)
+    dL0_dP0 = (n1 / P0t - n0 / (1.0 - P0t)) if in0 else np.zeros_like(n1)
+    L1 = t1.sum(axis=1)
+    a = logpsi + L1
+    b = log1mpsi + L0
+    ell = np.logaddexp(a, b)
+    r = expit(a - b)
+    d_eta = np.where(in_psi, r - psi, 0.0)
+    g_beta = np.concatenate([[d_eta.sum()], X.T @ d_eta])
+    d_nu = r[:, None] * dt1_dnu
+    g_alpha = np.concatenate([[d_nu.sum()], np.einsum("uj,ujk->k", d_nu, W)])
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+        g_beta = g_beta - beta
+        g_alpha = g_alpha - alpha
+    grads = [g_beta, g_alpha]
+    if fp_constant:
+        dl_dc = (r * np.sum(dt1_dc, axis=1)).sum() + ((1 - r) * dL0_dP0).sum() * (1.0 - u)
+        grads.append([dl_dc * c * (1 - c) + (dc if prior else 0.0)])
+    if fp_unoccupied:
+        dl_du = ((1 - r) * dL0_dP0).sum() * (1.0 - c)
+        grads.append([dl_du * u * (1 - u) + (du if prior else 0.0)])
+    logp = float(lp + ell.sum())
+    grad = np.concatenate([np.atleast_1d(g) for g in grads]).astype(np.float64)
+    if return_site_terms:
+        return logp, grad, dict(ell=ell, r=r, psi=psi, eta=eta, nu=nu)
+    return logp, grad
+
+
+def occu_rn_logp_grad(
+    theta, pr: Prepared, *, max_abundance=100, fp_constant=False, dtype=np.float32,
+    prior=True, return_site_terms=False,
+):
+    """Closed-form Royle-Nichols log-density + gradient."""
+    finfo = _finfo(dtype)
+    X, W, T, y, m = _units(pr)
+    Ks, Ko = X.shape[1], W.shape[2]
+    beta, alpha, xc, _ = split_theta(theta, Ks, Ko, fp_constant, False)
+    c = 0.0
+    lp = 0.0
+    if fp_constant:
+        c, l, dc = _extras_prior_sigmoid(xc)
+        lp += l if prior else 0.0
+    K = int(max_abundance)
+    k = np.arange(K + 1, dtype=np.float64)
+    eta = beta[0] + X @ beta[1:]
+    lam = np.exp(eta)
+    logits = xlogy(k[None, :], lam[:, None]) - gammaln(k + 1.0)[None, :] - lam[:, None]  # (U,K+1)
+    log_pi = logits - logsumexp(logits, axis=1, keepdims=True)
+    pi = np.exp(log_pi)
+    nu = alpha[0] + W @ alpha[1:]
+    r = expit(nu)
+    uj = -_softplus(nu)  # log(1-r)
+    # log(1 - P_kj) = k*log(1-r_j) + log(1-c), exact in log space (see _bern_terms_from_log1mP)
+    lq = k[None, None, :] * uj[:, :, None] + np.log1p(-c)  # (U,J,K+1)
+    t, dt_dnu, dt_dc = _bern_terms_from_log1mP(
+        lq, y[:, :, None], m[:, :, None], finfo,
+        dlq_dnu=-(k[None, None, :] * r[:, :, None]), dlq_dc=-1.0 / (1.0 - c))
+    A = log_pi + t.sum(axis=1)  # (U,K+1)
+    ell = logsumexp(A, axis=1)
+    w = np.exp(A - ell[:, None])
+    d_eta = (w * k).sum(axis=1) - (pi * k).sum(axis=1)
+    d_nu = np.einsum("uk,ujk->uj", w, dt_dnu)
+    g_beta = np.concatenate([[d_eta.sum()], X.T @ d_eta])
+    g_alpha = np.concatenate([[d_nu.sum()], np.einsum("uj,ujk->k", d_nu, W)])
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+        g_beta = g_beta - beta
+        g_alpha = g_alpha - alpha
+    grads = [g_beta, g_alpha]
+    if fp_constant:
+        dl_dc = np.einsum("uk,ujk->", w, dt_dc)
+        grads.append([dl_dc * c * (1 - c) + (dc if prior else 0.0)])
+    logp = float(lp + ell.sum())
+    grad = np.concatenate([np.atleast_1d(g) for g in grads]).astype(np.float64)
+    if return_site_terms:
+        return logp, grad, dict(ell=ell, w=w, eta=eta, nu=nu)
+    return logp, grad
+
+
+def occu_cop_logp_grad(
+    theta, pr: Prepared, *, fp_constant=False, fp_unoccupied=False, dtype=np.float32,
+    prior=True, return_site_terms=False,
+):
+    """Closed-form count-detection occupancy log-density + gradient."""
+    finfo = _finfo(dtype)
+    X, W, T, y, m = _units(pr)
+    Ks, Ko = X.shape[1], W.shape[2]
+    beta, alpha, xc, xu = split_theta(theta, Ks, Ko, fp_constant, fp_unoccupied)
+    c = u = 0.0
+    lp = 0.0
+    if fp_constant:
+        c, l, dc = _extras_prior_exp(xc)
+        lp += l if prior else 0.0
+    if fp_unoccupied:
+        u, l, du = _extras_prior_exp(xu)
+        lp += l if prior else 0.0
+    eta = beta[0] + X @ beta[1:]
+    psi, logpsi, log1mpsi, in_psi = _clamped_log_sigmoid_pair(eta, finfo)
+    nu = alpha[0] + W @ alpha[1:]
+    mu = np.exp(nu)
+    rho1 = mu + c
+    rho0 = u + c
+    lg = gammaln(y + 1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1 = np.where(m, xlogy(y, T * rho1) - lg - T * rho1, 0.0)
+        t0 = np.where(m, xlogy(y, T * rho0) - lg - T * rho0, 0.0)
+        d1 = np.where(m, np.where(y > 0, y / rho1, 0.0) - T, 0.0)  # d t1 / d rho1
+        d0 = np.where(m, (np.where(y > 0, y / rho0, 0.0) if rho0 > 0 else 0.0) - T, 0.0)
+    a = logpsi + t1.sum(axis=1)
+    b = log1mpsi + t0.sum(axis=1)
+    ell = np.logaddexp(a, b)
+    with np.errstate(invalid="ignore"):
+        r = np.where(np.isneginf(b), 1.0, expit(a - b))
+    d_eta = np.where(in_psi, r - psi, 0.0)
+    d_nu = r[:, None] * d1 * mu
+    g_beta = np.concatenate([[d_eta.sum()], X.T @ d_eta])
+    g_alpha = np.concatenate([[d_nu.sum()], np.einsum("uj,ujk->k", d_nu, W)])
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+        g_beta = g_beta - beta
+        g_alpha = g_alpha - alpha
+    grads = [g_beta, g_alpha]
+    s1 = d1.sum(axis=1)
+    s0 = np.where(r < 1.0, d0.sum(axis=1), 0.0)
+    if fp_constant:
+        dl_dc = (r * s1 + (1 - r) * s0).sum()
+        grads.append([dl_dc * c + (dc if prior else 0.0)])
+    if fp_unoccupied:
+        dl_du = ((1 - r) * s0).sum()
+        grads.append([dl_du * u + (du if prior else 0.0)])
+    logp = float(lp + ell.sum())
+    grad = np.concatenate([np.atleast_1d(g) for g in grads]).astype(np.float64)
+    if return_site_terms:
+        return logp, grad, dict(ell=ell, r=r, psi=psi, eta=eta, nu=nu)
+    return logp, grad
+
+
+# ------------------------------------------------------------------ conveniences
+def logp_grad(model: str, theta, pr: Prepared, **kw):
+    """Dispatch on model name; theta (D,) or (C, D) -> (logp[C], grad[C,D])."""
+    fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad}[model]
+    theta = np.asarray(theta, np.float64)
+    if theta.ndim == 1:
+        return fn(theta, pr, **kw)
+    out = [fn(t, pr, **kw) for t in theta]
+    return np.array([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def log_joint_enumerated(model: str, theta, data: dict, **kw):
+    fn = {
+        "occu": occu_log_joint_enumerated,
+        "occu_rn": occu_rn_log_joint_enumerated,
+        "occu_cop": occu_cop_log_joint_enumerated,
+    }[model]
+    args = [data["site_covs"], data["obs_covs"], data["obs"]]
+    if model == "occu_cop":
+        args.append(data.get("session_duration"))
+    return fn(theta, *args, **kw)
+
+
+def finite_difference_grad(f, theta, h=1e-6):
+    theta = np.asarray(theta, np.float64)
+    g = np.zeros_like(theta)
+    for i in range(theta.size):
+        e = np.zeros_like(theta)
+        e[i] = h * max(1.0, abs(theta[i]))
+        g[i] = (f(theta + e) - f(theta - e)) / (2 * e[i])
+    return g
+
+
+def expected_mask(site_covs, obs_covs, obs) -> np.ndarray:
+    """The bit-exact mask contract: (Sp,S,P,J) bool."""
+    site_covs = np.asarray(site_covs)
+    obs_covs = np.asarray(obs_covs)
+    obs = np.asarray(obs)
+    cov_nan = np.isnan(obs_covs).any(axis=-1) | np.isnan(site_covs).any(axis=-1)[:, None, None]
+    return np.isfinite(obs) & ~cov_nan[None, ...]
