@@ -1,0 +1,479 @@
+// C ABI of libbiolith_b200.so (declared in include/biolith_b200.h).  Plain pointers and sizes only.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "engine.cuh"
+#include "handle.h"
+
+namespace bl {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// kernels defined in the per-model translation units
+cudaError_t launch_pack(int data_dtype, int dtype, const void* y, const void* X, const void* W, const void* T,
+                        void* out, const Layout& L, int model, int* err_flag, unsigned long long* n_masked,
+                        cudaStream_t st);
+cudaError_t launch_export_mask(int dtype, const void* packed, uint8_t* mask, const Layout& L, cudaStream_t st);
+cudaError_t launch_occu(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
+cudaError_t launch_occu_rn(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
+cudaError_t launch_occu_cop(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
+int occu_has_specialisation(int ks, int ko, bool fp);
+int occu_derived_slots(uint32_t flags);
+int occu_rn_derived_slots(uint32_t flags);
+int occu_cop_derived_slots(uint32_t flags);
+size_t occu_rn_extra_smem(const Layout& L, int K, int elem);
+
+static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st,
+                                int* occ) {
+  switch (ds->desc.model) {
+    case BL_MODEL_OCCU: return launch_occu(p, ds->desc.dtype, grid, smem, st, occ);
+    case BL_MODEL_OCCU_RN: return launch_occu_rn(p, ds->desc.dtype, grid, smem, st, occ);
+    default: return launch_occu_cop(p, ds->desc.dtype, grid, smem, st, occ);
+  }
+}
+
+static size_t elem_size(int dtype) { return dtype == BL_F32 ? 4 : 8; }
+
+static void fill_params(const bl_dataset* ds, EvalParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.packed = ds->packed;
+  p.L = ds->L;
+  p.model = ds->desc.model;
+  p.D = ds->D;
+  p.DS = ds->DS;
+  p.NQ = 1 + ds->D;
+  p.flags = ds->desc.flags;
+  p.K = ds->desc.max_abundance;
+  p.cop_const = ds->cop_const;
+  p.prior_beta_loc = ds->desc.prior_beta_loc;
+  p.prior_beta_scale = ds->desc.prior_beta_scale;
+  p.prior_alpha_loc = ds->desc.prior_alpha_loc;
+  p.prior_alpha_scale = ds->desc.prior_alpha_scale;
+  p.prior_fp_a = ds->desc.prior_fp_a;
+  p.prior_fp_b = ds->desc.prior_fp_b;
+  p.prior_fp_rate = ds->desc.prior_fp_rate;
+}
+
+// geometry for C chains (cached); grows the fp64 partial workspace when needed
+static int plan_for(bl_dataset* ds, int C, Plan** out) {
+  auto it = ds->plans.find(C);
+  if (it == ds->plans.end()) {
+    Plan pl{};
+    const int elem = (int)elem_size(ds->desc.dtype);
+    size_t extra = 0;
+    if (ds->desc.model == BL_MODEL_OCCU_RN) extra = occu_rn_extra_smem(ds->L, ds->desc.max_abundance, elem);
+    pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit - 2 * extra);
+    pl.g.smem_bytes += extra;
+    if (pl.g.smem_bytes > ds->smem_limit)
+      return fail(BL_ERR_UNSUPPORTED, "shape needs %zu B of shared memory per block (> %zu)", pl.g.smem_bytes,
+                  ds->smem_limit);
+    EvalParams p;
+    fill_params(ds, p);
+    int occ = 0;
+    cudaError_t e = launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
+    if (e != cudaSuccess) return fail(BL_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
+    if (occ < 1) return fail(BL_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", pl.g.smem_bytes);
+    pl.occupancy = occ;
+    int64_t want = (int64_t)ds->num_sms * occ / pl.g.n_chunks;
+    if (want < 1) want = 1;
+    pl.g.nsplit = (int)(want < pl.g.n_block_tiles ? want : pl.g.n_block_tiles);
+    if (pl.g.nsplit < 1) pl.g.nsplit = 1;
+    it = ds->plans.emplace(C, pl).first;
+  }
+  Plan& pl = it->second;
+  const size_t need = (size_t)pl.g.nsplit * C * (1 + ds->D);
+  if (need > ds->partial_cap || (size_t)pl.g.n_chunks > ds->counters_cap || (size_t)C > ds->sums_cap) {
+    // (re)allocation synchronises; callers that must not sync pass desc.max_chains up front
+    cudaDeviceSynchronize();
+    if (need > ds->partial_cap) {
+      cudaFree(ds->partial);
+      if (cudaMalloc(&ds->partial, need * sizeof(double)) != cudaSuccess)
+        return fail(BL_ERR_NOMEM, "cudaMalloc(partials, %zu B) failed", need * sizeof(double));
+      ds->partial_cap = need;
+    }
+    if ((size_t)pl.g.n_chunks > ds->counters_cap) {
+      cudaFree(ds->counters);
+      size_t n = (size_t)pl.g.n_chunks + 16;
+      if (cudaMalloc(&ds->counters, n * sizeof(unsigned int)) != cudaSuccess) return fail(BL_ERR_NOMEM, "counters");
+      cudaMemset(ds->counters, 0, n * sizeof(unsigned int));
+      ds->counters_cap = n;
+    }
+    if ((size_t)C > ds->sums_cap) {
+      cudaFree(ds->sums);
+      if (cudaMalloc(&ds->sums, (size_t)C * (1 + ds->D) * sizeof(double)) != cudaSuccess)
+        return fail(BL_ERR_NOMEM, "sums");
+      ds->sums_cap = C;
+    }
+  }
+  *out = &pl;
+  return BL_OK;
+}
+
+int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce) {
+  Plan* pl = nullptr;
+  int rc = plan_for(ds, C, &pl);
+  if (rc) return rc;
+  EvalParams p;
+  fill_params(ds, p);
+  p.theta = theta;
+  p.logp = logp;
+  p.grad = grad;
+  p.partial = ds->partial;
+  p.counters = ds->counters;
+  p.sums = ds->sums;
+  p.allreduce = allreduce;
+  p.C = C;
+  p.CB = pl->g.CB;
+  p.WC = pl->g.WC;
+  p.WS = pl->g.WS;
+  p.nstage = pl->g.nstage;
+  p.nsplit = pl->g.nsplit;
+  p.n_block_tiles = pl->g.n_block_tiles;
+  cudaError_t e = launch_model(ds, p, dim3(pl->g.nsplit, pl->g.n_chunks), pl->g.smem_bytes, st, nullptr);
+  if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return BL_OK;
+}
+
+}  // namespace bl
+
+using namespace bl;
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) return fail(BL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));     \
+  } while (0)
+
+extern "C" {
+
+int bl_version(void) { return BL_ABI_VERSION; }
+
+const char* bl_strerror(int status) {
+  switch (status) {
+    case BL_OK: return "ok";
+    case BL_ERR_INVALID: return "invalid argument";
+    case BL_ERR_UNSUPPORTED: return "option outside the accelerated path (no fallback)";
+    case BL_ERR_CUDA: return "CUDA error";
+    case BL_ERR_NCCL: return "NCCL error";
+    case BL_ERR_BAD_DATA: return "bad data";
+    case BL_ERR_NOMEM: return "out of memory";
+    default: return "unknown";
+  }
+}
+
+const char* bl_last_error(void) { return g_err; }
+
+int bl_device_count(int* count) {
+  if (!count) return fail(BL_ERR_INVALID, "count is NULL");
+  *count = 0;
+  CU_TRY(cudaGetDeviceCount(count));
+  return BL_OK;
+}
+
+int64_t bl_launch_count(void) { return g_launches.load(); }
+
+int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void* W, const void* T,
+                      bl_dataset** out) {
+  if (!d || !out) return fail(BL_ERR_INVALID, "desc/out is NULL");
+  *out = nullptr;
+  if (d->abi_version != BL_ABI_VERSION) return fail(BL_ERR_INVALID, "ABI version %d != %d", d->abi_version, BL_ABI_VERSION);
+  if (d->model < 0 || d->model > 2) return fail(BL_ERR_INVALID, "unknown model %d", d->model);
+  if ((d->dtype != BL_F32 && d->dtype != BL_F64) || (d->data_dtype != BL_F32 && d->data_dtype != BL_F64))
+    return fail(BL_ERR_INVALID, "dtype must be BL_F32 or BL_F64");
+  if (d->n_sites < 0 || d->n_periods < 1 || d->n_replicates < 1 || d->n_site_covs < 0 || d->n_obs_covs < 0)
+    return fail(BL_ERR_INVALID, "bad shape S=%lld P=%d J=%d Ks=%d Ko=%d", (long long)d->n_sites, d->n_periods,
+                d->n_replicates, d->n_site_covs, d->n_obs_covs);
+  if (d->n_species != 1) return fail(BL_ERR_UNSUPPORTED, "n_species=%d: one handle per species", d->n_species);
+  if (d->n_site_covs > kMaxCov || d->n_obs_covs > kMaxCov)
+    return fail(BL_ERR_UNSUPPORTED, "more than %d covariates per predictor", kMaxCov);
+  const bool fpc = d->flags & BL_FLAG_FP_CONSTANT, fpu = d->flags & BL_FLAG_FP_UNOCCUPIED;
+  if (d->model == BL_MODEL_OCCU && fpc && fpu)
+    return fail(BL_ERR_INVALID, "false_positives_constant and false_positives_unoccupied cannot both be True");  // occu.py:112-114
+  if (d->model == BL_MODEL_OCCU_RN && fpu) return fail(BL_ERR_INVALID, "occu_rn has no false_positives_unoccupied");
+  if (d->model == BL_MODEL_OCCU_RN && (d->max_abundance < 1 || d->max_abundance > 1023))
+    return fail(BL_ERR_INVALID, "max_abundance must be in [1, 1023]");
+  if (d->n_sites > 0 && (!y || !X || !W)) return fail(BL_ERR_INVALID, "y/X/W is NULL");
+  if ((d->flags & BL_FLAG_PRIOR) && (d->prior_beta_scale <= 0 || d->prior_alpha_scale <= 0))
+    return fail(BL_ERR_INVALID, "prior scales must be positive");
+
+  CU_TRY(cudaSetDevice(d->device));
+  bl_dataset* ds = new (std::nothrow) bl_dataset();
+  if (!ds) return fail(BL_ERR_NOMEM, "host allocation failed");
+  ds->desc = *d;
+  ds->L = make_layout(d->model, d->n_sites, d->n_periods, d->n_replicates, d->n_site_covs, d->n_obs_covs);
+  ds->n_extras = (fpc ? 1 : 0) + (fpu ? 1 : 0);
+  ds->D = d->n_site_covs + 1 + d->n_obs_covs + 1 + ds->n_extras;
+  int derived = d->model == BL_MODEL_OCCU ? occu_derived_slots(d->flags)
+                : d->model == BL_MODEL_OCCU_RN ? occu_rn_derived_slots(d->flags) : occu_cop_derived_slots(d->flags);
+  ds->DS = ds->D + derived;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
+  if (e != cudaSuccess) { delete ds; return fail(BL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  ds->num_sms = prop.multiProcessorCount;
+  ds->smem_limit = prop.sharedMemPerBlockOptin;
+
+  const Layout& L = ds->L;
+  const size_t es = elem_size(d->dtype), ds_in = elem_size(d->data_dtype);
+  ds->packed_bytes = (size_t)L.n_tiles_padded * L.F * kWarp * es;
+  if (ds->packed_bytes == 0) ds->packed_bytes = 16;
+  void *dy = nullptr, *dX = nullptr, *dW = nullptr, *dT = nullptr;
+  int* d_err = nullptr;
+  unsigned long long* d_nm = nullptr;
+  const size_t nobs = (size_t)L.n_units * L.J;
+  int rc = BL_OK;
+  do {
+#define CU_BRK(expr)                                                                   \
+    if ((e = (expr)) != cudaSuccess) { rc = fail(BL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e)); break; }
+    CU_BRK(cudaMalloc(&ds->packed, ds->packed_bytes));
+    CU_BRK(cudaMemset(ds->packed, 0, ds->packed_bytes));
+    CU_BRK(cudaMalloc(&d_err, sizeof(int)));
+    CU_BRK(cudaMemset(d_err, 0, sizeof(int)));
+    CU_BRK(cudaMalloc(&d_nm, sizeof(unsigned long long)));
+    CU_BRK(cudaMemset(d_nm, 0, sizeof(unsigned long long)));
+    if (L.n_units > 0) {
+      CU_BRK(cudaMalloc(&dy, nobs * ds_in));
+      CU_BRK(cudaMalloc(&dX, (size_t)d->n_sites * (L.ks > 0 ? L.ks : 1) * ds_in));
+      CU_BRK(cudaMalloc(&dW, nobs * (L.ko > 0 ? L.ko : 1) * ds_in));
+      CU_BRK(cudaMemcpy(dy, y, nobs * ds_in, cudaMemcpyDefault));
+      if (L.ks > 0) CU_BRK(cudaMemcpy(dX, X, (size_t)d->n_sites * L.ks * ds_in, cudaMemcpyDefault));
+      if (L.ko > 0) CU_BRK(cudaMemcpy(dW, W, nobs * L.ko * ds_in, cudaMemcpyDefault));
+      if (T && d->model == BL_MODEL_OCCU_COP) {
+        CU_BRK(cudaMalloc(&dT, nobs * ds_in));
+        CU_BRK(cudaMemcpy(dT, T, nobs * ds_in, cudaMemcpyDefault));
+      }
+      CU_BRK(launch_pack(d->data_dtype, d->dtype, dy, dX, dW, dT, ds->packed, L, d->model, d_err, d_nm, nullptr));
+      g_launches.fetch_add(1);
+      CU_BRK(cudaDeviceSynchronize());
+    }
+    int h_err = 0;
+    unsigned long long h_nm = 0;
+    CU_BRK(cudaMemcpy(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    CU_BRK(cudaMemcpy(&h_nm, d_nm, sizeof(h_nm), cudaMemcpyDeviceToHost));
+    ds->n_masked = (int64_t)h_nm;
+    if (h_err & 1) { rc = fail(BL_ERR_BAD_DATA, "detections must be binary (0/1) or non-finite (missing)"); break; }
+    if (h_err & 2) { rc = fail(BL_ERR_BAD_DATA, "counts must be >= 0 and session_duration finite"); break; }
+#undef CU_BRK
+  } while (0);
+  cudaFree(dy); cudaFree(dX); cudaFree(dW); cudaFree(dT); cudaFree(d_err); cudaFree(d_nm);
+  if (rc == BL_OK && d->model == BL_MODEL_OCCU_COP) {
+    // data-only constant  sum m (y log T - lgamma(y+1)), in double, fixed order (host arrays only)
+    double acc = 0.0;
+    auto rd = [&](const void* a, size_t i) -> double {
+      return d->data_dtype == BL_F32 ? (double)((const float*)a)[i] : ((const double*)a)[i];
+    };
+    auto rd_c = [&](const void* a, size_t i) -> double {  // value as the compute dtype sees it
+      double v = rd(a, i);
+      return d->dtype == BL_F32 ? (double)(float)v : v;
+    };
+    for (int64_t u = 0; u < L.n_units; ++u) {
+      const int64_t s = u / L.P;
+      bool site_nan = false;
+      for (int k = 0; k < L.ks; ++k) site_nan |= std::isnan(rd(X, (size_t)s * L.ks + k));
+      for (int j = 0; j < L.J; ++j) {
+        const size_t o = (size_t)u * L.J + j;
+        bool cov_nan = site_nan;
+        for (int k = 0; k < L.ko; ++k) cov_nan |= std::isnan(rd(W, o * L.ko + k));
+        const double yv = rd_c(y, o);
+        if (!std::isfinite(yv) || cov_nan) continue;
+        const double tv = T ? rd_c(T, o) : 1.0;
+        acc += (yv > 0 ? yv * std::log(tv) : 0.0) - std::lgamma(yv + 1.0);
+      }
+    }
+    ds->cop_const = acc;
+  }
+  if (rc == BL_OK) {
+    cudaError_t e2 = cudaStreamCreateWithFlags(&ds->own_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&ds->ev0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&ds->ev1);
+    if (e2 != cudaSuccess) rc = fail(BL_ERR_CUDA, "stream/event create: %s", cudaGetErrorString(e2));
+  }
+  if (rc == BL_OK && d->max_chains > 0) {
+    Plan* pl = nullptr;
+    rc = plan_for(ds, d->max_chains, &pl);
+  }
+  if (rc != BL_OK) { bl_dataset_destroy(ds); return rc; }
+  *out = ds;
+  return BL_OK;
+}
+
+int bl_dataset_destroy(bl_dataset* ds) {
+  if (!ds) return BL_OK;
+  cudaSetDevice(ds->desc.device);
+  cudaFree(ds->packed); cudaFree(ds->partial); cudaFree(ds->counters); cudaFree(ds->sums);
+  cudaFree(ds->d_theta); cudaFree(ds->d_out);
+  if (ds->h_theta) cudaFreeHost(ds->h_theta);
+  if (ds->h_out) cudaFreeHost(ds->h_out);
+  if (ds->ev0) cudaEventDestroy(ds->ev0);
+  if (ds->ev1) cudaEventDestroy(ds->ev1);
+  if (ds->own_stream) cudaStreamDestroy(ds->own_stream);
+  delete ds;
+  return BL_OK;
+}
+
+int bl_dataset_info(const bl_dataset* ds, bl_info* info) {
+  if (!ds || !info) return fail(BL_ERR_INVALID, "NULL argument");
+  const Layout& L = ds->L;
+  const int64_t es = (int64_t)elem_size(ds->desc.dtype);
+  info->theta_dim = ds->D;
+  info->n_extras = ds->n_extras;
+  info->n_units = L.n_units;
+  info->packed_bytes = (int64_t)ds->packed_bytes;
+  // bytes(y) + bytes(X) + bytes(W) (+ bytes(T)) + theta + (logp, grad), in the compute dtype
+  int64_t per_unit = L.J + (int64_t)L.J * L.ko + (ds->desc.model == BL_MODEL_OCCU_COP ? L.J : 0);
+  info->algorithmic_bytes = es * (L.n_units * per_unit + ds->desc.n_sites * L.ks) + es * (2 * ds->D + 1);
+  info->n_masked = ds->n_masked;
+  info->fields_per_unit = L.F;
+  const bool fp = ds->n_extras > 0;
+  info->kernel_variant = ds->desc.model == BL_MODEL_OCCU ? occu_has_specialisation(L.ks, L.ko, fp) : 0;
+  return BL_OK;
+}
+
+int bl_dataset_export_mask(const bl_dataset* ds, uint8_t* mask_out) {
+  if (!ds || !mask_out) return fail(BL_ERR_INVALID, "NULL argument");
+  const size_t n = (size_t)ds->L.n_units * ds->L.J;
+  if (n == 0) return BL_OK;
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  uint8_t* d_mask = nullptr;
+  CU_TRY(cudaMalloc(&d_mask, n));
+  cudaError_t e = launch_export_mask(ds->desc.dtype, ds->packed, d_mask, ds->L, nullptr);
+  g_launches.fetch_add(1);
+  if (e == cudaSuccess) e = cudaMemcpy(mask_out, d_mask, n, cudaMemcpyDeviceToHost);
+  cudaFree(d_mask);
+  if (e != cudaSuccess) return fail(BL_ERR_CUDA, "export mask: %s", cudaGetErrorString(e));
+  return BL_OK;
+}
+
+int bl_eval(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp, void* grad, bl_stream stream) {
+  if (!ds || !theta || !logp || !grad) return fail(BL_ERR_INVALID, "NULL argument");
+  if (n_chains < 1) return fail(BL_ERR_INVALID, "n_chains must be >= 1");
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  return eval_device(ds, theta, n_chains, logp, grad, (cudaStream_t)stream, 0);
+}
+
+static int ensure_host_staging(bl_dataset* ds, int C) {
+  if (C <= ds->host_cap) return BL_OK;
+  const size_t es = elem_size(ds->desc.dtype);
+  cudaDeviceSynchronize();
+  cudaFree(ds->d_theta); cudaFree(ds->d_out);
+  if (ds->h_theta) cudaFreeHost(ds->h_theta);
+  if (ds->h_out) cudaFreeHost(ds->h_out);
+  ds->d_theta = ds->d_out = ds->h_theta = ds->h_out = nullptr;
+  ds->host_cap = 0;
+  const size_t nt = (size_t)C * ds->D * es, no = (size_t)C * (1 + ds->D) * es;
+  CU_TRY(cudaMalloc(&ds->d_theta, nt));
+  CU_TRY(cudaMalloc(&ds->d_out, no));
+  CU_TRY(cudaMallocHost(&ds->h_theta, nt));
+  CU_TRY(cudaMallocHost(&ds->h_out, no));
+  ds->host_cap = C;
+  return BL_OK;
+}
+
+int bl_eval_host(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp, void* grad) {
+  if (!ds || !theta || !logp || !grad) return fail(BL_ERR_INVALID, "NULL argument");
+  if (n_chains < 1) return fail(BL_ERR_INVALID, "n_chains must be >= 1");
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  int rc = ensure_host_staging(ds, n_chains);
+  if (rc) return rc;
+  const size_t es = elem_size(ds->desc.dtype);
+  const size_t nt = (size_t)n_chains * ds->D * es, nl = (size_t)n_chains * es;
+  cudaStream_t st = ds->own_stream;
+  memcpy(ds->h_theta, theta, nt);  // pageable caller buffer -> pinned staging
+  CU_TRY(cudaMemcpyAsync(ds->d_theta, ds->h_theta, nt, cudaMemcpyHostToDevice, st));
+  char* d_logp = (char*)ds->d_out;
+  char* d_grad = d_logp + nl;
+  rc = eval_device(ds, ds->d_theta, n_chains, d_logp, d_grad, st, 0);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(ds->h_out, ds->d_out, nl + nt, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  memcpy(logp, ds->h_out, nl);
+  memcpy(grad, (char*)ds->h_out + nl, nt);
+  return BL_OK;
+}
+
+int bl_eval_timed(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp, void* grad, bl_stream stream,
+                  int32_t iters, float* ms_per_eval) {
+  if (!ds || !ms_per_eval || iters < 1) return fail(BL_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU_TRY(cudaEventRecord(ds->ev0, st));
+  for (int i = 0; i < iters; ++i) {
+    int rc = bl_eval(ds, theta, n_chains, logp, grad, stream);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaEventRecord(ds->ev1, st));
+  CU_TRY(cudaEventSynchronize(ds->ev1));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, ds->ev0, ds->ev1));
+  *ms_per_eval = ms / iters;
+  return BL_OK;
+}
+
+int bl_device_malloc(int32_t device, size_t bytes, void** ptr) {
+  if (!ptr) return fail(BL_ERR_INVALID, "ptr is NULL");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaMalloc(ptr, bytes ? bytes : 16));
+  return BL_OK;
+}
+int bl_device_free(void* ptr) { CU_TRY(cudaFree(ptr)); return BL_OK; }
+int bl_memcpy_h2d(void* dst, const void* src, size_t bytes, bl_stream stream) {
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return BL_OK;
+}
+int bl_memcpy_d2h(void* dst, const void* src, size_t bytes, bl_stream stream) {
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return BL_OK;
+}
+int bl_host_malloc_pinned(size_t bytes, void** ptr) {
+  if (!ptr) return fail(BL_ERR_INVALID, "ptr is NULL");
+  CU_TRY(cudaMallocHost(ptr, bytes ? bytes : 16));
+  return BL_OK;
+}
+int bl_host_free_pinned(void* ptr) { CU_TRY(cudaFreeHost(ptr)); return BL_OK; }
+int bl_stream_create(int32_t device, bl_stream* stream) {
+  if (!stream) return fail(BL_ERR_INVALID, "stream is NULL");
+  CU_TRY(cudaSetDevice(device));
+  cudaStream_t s;
+  CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (bl_stream)s;
+  return BL_OK;
+}
+int bl_stream_destroy(bl_stream stream) { CU_TRY(cudaStreamDestroy((cudaStream_t)stream)); return BL_OK; }
+int bl_stream_sync(bl_stream stream) { CU_TRY(cudaStreamSynchronize((cudaStream_t)stream)); return BL_OK; }
+
+int bl_flush_l2(int32_t device, bl_stream stream) {
+  static std::mutex mu;
+  static std::map<int, void*> bufs;
+  const size_t bytes = 256u << 20;  // > 126 MB L2
+  CU_TRY(cudaSetDevice(device));
+  void* buf = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = bufs.find(device);
+    if (it == bufs.end()) {
+      CU_TRY(cudaMalloc(&buf, bytes));
+      bufs[device] = buf;
+    } else {
+      buf = it->second;
+    }
+  }
+  CU_TRY(cudaMemsetAsync(buf, 0, bytes, (cudaStream_t)stream));
+  return BL_OK;
+}
+
+}  // extern "C"

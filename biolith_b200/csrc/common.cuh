@@ -1,0 +1,223 @@
+// Shared device helpers: TMA bulk-copy / mbarrier PTX, math traits, warp reductions, and the
+// dataset handle.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include "../../include/biolith_b200.h"
+
+namespace bl {
+
+constexpr int kWarp = 32;
+constexpr int kBlockThreads = 256;            // 8 warps, arranged WS site-groups x WC chain-groups
+constexpr int kWarpsPerBlock = kBlockThreads / kWarp;
+constexpr int kMaxChainsPerBlock = 256;       // chain chunk handled by one block (grid.y splits the rest)
+constexpr int kMaxCov = 16;                   // generic kernel: Ks, Ko <= 16
+constexpr int kMaxStages = 4;
+
+// ------------------------------------------------------------------------------------------
+// packed dataset layout (built once by pack.cu, consumed by every eval kernel)
+//
+//   unit u = s * P + p                      (site-major, period minor; each unit is an independent
+//                                            marginalisation over z / N, occu.py:204-210)
+//   warp-tile t = u / 32, lane = u % 32
+//   tile t occupies F * 32 elements:  field f of lane l at  t*F*32 + f*32 + l     ("SoA in tile")
+//   fields:  [0, Ks)                 X_k               (NaN -> 0, +-inf -> +-max)
+//            [Ks, Ks + J*Ko)         W_{j,k} at Ks + j*Ko + k
+//            occu / occu_rn:  NW = ceil(J/32) words of y bits, then NW words of mask bits
+//            occu_cop:        J floats y (0 if masked), J floats T (0 if masked), Sy, ST, NW mask words
+//   every warp-wide read of one field is one coalesced 128-byte (fp32) line, and a whole tile is a
+//   contiguous, 16-byte aligned chunk -> one cp.async.bulk (TMA) per block-tile.
+// ------------------------------------------------------------------------------------------
+struct Layout {
+  int ks, ko, J, P;
+  int nw;          // bit words per unit
+  int F;           // fields per unit
+  int off_w;       // first W field
+  int off_y;       // y bits (occu/rn) or y floats (cop)
+  int off_m;       // mask bit words
+  int off_t;       // cop: T floats
+  int off_sy;      // cop: sum of masked y; +1 = sum of masked T
+  int64_t n_units; // S*P
+  int64_t n_tiles; // ceil(n_units/32)
+  int64_t n_tiles_padded;  // multiple of kWarpsPerBlock so any block-tile TMA stays in bounds
+};
+
+inline Layout make_layout(int model, int64_t S, int P, int J, int ks, int ko) {
+  Layout L{};
+  L.ks = ks; L.ko = ko; L.J = J; L.P = P;
+  L.nw = (J + 31) / 32;
+  L.off_w = ks;
+  int f = ks + J * ko;
+  if (model == BL_MODEL_OCCU_COP) {
+    L.off_y = f; f += J;
+    L.off_t = f; f += J;
+    L.off_sy = f; f += 2;
+    L.off_m = f; f += L.nw;
+  } else {
+    L.off_y = f; f += L.nw;
+    L.off_m = f; f += L.nw;
+    L.off_t = -1; L.off_sy = -1;
+  }
+  L.F = f;
+  L.n_units = S * (int64_t)P;
+  L.n_tiles = (L.n_units + 31) / 32;
+  L.n_tiles_padded = (L.n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------
+// math traits: constants follow numpyro's clamp_probs(finfo.tiny, 1 - finfo.eps) per dtype
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Num;
+
+template <> struct Num<float> {
+  using bits_t = uint32_t;
+  static __device__ __forceinline__ float log_tiny() { return -87.33654475055310898657f; }   // log(FLT_MIN)
+  static __device__ __forceinline__ float log_eps() { return -15.94238515333216719f; }       // log(FLT_EPSILON)
+  static __device__ __forceinline__ float log1m_eps() { return -1.1920929665620861e-07f; }   // log1p(-eps)
+  static __device__ __forceinline__ float neg_tiny() { return -FLT_MIN; }                    // log1p(-tiny)
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float log_(float x) { return logf(x); }
+  static __device__ __forceinline__ float log1p_(float x) { return log1pf(x); }
+  static __device__ __forceinline__ float expm1_(float x) { return expm1f(x); }
+  static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+  static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+  static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
+  static __device__ __forceinline__ uint32_t as_bits(float x) { return __float_as_uint(x); }
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+
+template <> struct Num<double> {
+  using bits_t = uint64_t;
+  static __device__ __forceinline__ double log_tiny() { return -708.3964185322641; }          // log(DBL_MIN)
+  static __device__ __forceinline__ double log_eps() { return -36.04365338911715; }           // log(DBL_EPSILON)
+  static __device__ __forceinline__ double log1m_eps() { return -2.2204460492503136e-16; }
+  static __device__ __forceinline__ double neg_tiny() { return -DBL_MIN; }
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double log_(double x) { return log(x); }
+  static __device__ __forceinline__ double log1p_(double x) { return log1p(x); }
+  static __device__ __forceinline__ double expm1_(double x) { return expm1(x); }
+  static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+  static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+  static __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ uint32_t as_bits(double x) { return (uint32_t)__double_as_longlong(x); }
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+// Clamped log-sigmoid pair in log space (oracle/occupancy.py:_clamped_log_sigmoid_pair):
+//   p = sigmoid(x), p~ = clip(p, tiny, 1-eps);  lp = log p~, l1mp = log1p(-p~),
+//   in-range flag `inr` (derivatives are zero outside, like jnp.clip).
+template <typename T>
+struct LogSig {
+  T p, q;      // sigmoid(x), sigmoid(-x)
+  T lp, l1mp;  // clamped logs
+  bool inr;
+};
+
+template <typename T>
+__device__ __forceinline__ LogSig<T> log_sigmoid_pair(T x) {
+  using N = Num<T>;
+  LogSig<T> r;
+  const T t = N::exp_(-N::abs_(x));   // in (0, 1]
+  const T l = N::log1p_(t);
+  const T inv = N::rcp_(T(1) + t);
+  const T ti = t * inv;
+  const bool pos = x >= T(0);
+  r.p = pos ? inv : ti;
+  r.q = pos ? ti : inv;
+  T lp = N::min_(x, T(0)) - l;         // log sigmoid(x)
+  T l1 = -N::max_(x, T(0)) - l;        // log sigmoid(-x)
+  const bool lo = lp <= N::log_tiny();
+  const bool hi = l1 <= N::log_eps();
+  r.inr = !(lo || hi);
+  r.lp = lo ? N::log_tiny() : (hi ? N::log1m_eps() : lp);
+  r.l1mp = lo ? N::neg_tiny() : (hi ? N::log_eps() : l1);
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk) + mbarrier
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_bulk(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters shared by the three likelihood kernels
+// ------------------------------------------------------------------------------------------
+struct EvalParams {
+  const void* packed;      // packed dataset (element type = compute type)
+  const void* theta;       // [C][D]
+  void* logp;              // [C]
+  void* grad;              // [C][D]
+  double* partial;         // [nsplit][C][NQ] fp64 block partials
+  unsigned int* counters;  // [n_chunks] "blocks done" tickets (self-resetting)
+  Layout L;
+  int model;    // bl_model
+  int DS;       // stride of a staged theta row in shared memory (D + derived per-chain slots)
+  int C;        // chains in this call
+  int D;        // theta dim
+  int NQ;       // 1 + D
+  int CB;       // chains per block (chunk)
+  int WC, WS;   // warp arrangement: WC chain-groups x WS site-groups = 8 warps
+  int nstage;
+  int nsplit;   // grid.x
+  int64_t n_block_tiles;  // ceil(n_tiles / WS)
+  uint32_t flags;
+  int K;        // occu_rn: max_abundance
+  double cop_const;  // occu_cop: sum_s sum_j m (y log T - lgamma(y+1)), data-only
+  double prior_beta_loc, prior_beta_scale, prior_alpha_loc, prior_alpha_scale;
+  double prior_fp_a, prior_fp_b, prior_fp_rate;
+  int allreduce;  // 0 none; 1 = leave raw sums in `sums` for a collective, finalize separately
+  double* sums;   // [C][NQ] raw (un-prior'd) sums when allreduce != 0
+};
+
+}  // namespace bl

@@ -1,0 +1,228 @@
+// The site-tile engine shared by the occu / occu_rn / occu_cop likelihood kernels.
+//
+// Mapping (see DESIGN.md "kernel design"):
+//   lane  = unit (site x period)          -> every field read is one coalesced 128 B line
+//   warp  = (site-group ws, chain-group wc); a block of 8 warps is WS x WC
+//   block = (site split bx, chain chunk by); persistent over a contiguous range of block-tiles
+//   tile  = WS warp-tiles, staged HBM -> SMEM by ONE cp.async.bulk (TMA) per block-tile through an
+//           NSTAGE mbarrier ring, then re-used by every chain of the chunk (CB <= 256 chains).
+// Per (unit, chain) the Model functor returns NQ = 1 + D numbers (log-marginal, d/dtheta); they are
+// summed over the 32 lanes by xor-shuffles and accumulated in fp64 shared memory by a fixed owner
+// (warp (ws,wc) owns chains wc, wc+WC, ... of site-group ws) -> no atomics, deterministic order.
+// The last block of each chain chunk (ticket counter) reduces the per-split partials in split
+// order and writes logp / grad (+ priors): one launch per evaluation.
+#pragma once
+
+#include "common.cuh"
+
+namespace bl {
+
+// lgamma for small positive arguments used by the prior normaliser (host+device, double)
+__device__ __forceinline__ double log_sigmoid_d(double x) { return fmin(x, 0.0) - log1p(exp(-fabs(x))); }
+
+// Adds priors (+ Jacobians) to the raw sums of one chain and writes the outputs.
+template <typename T>
+__device__ void finalize_chain(const EvalParams& p, int c, int q, double total, bool add_const) {
+  const T* theta = reinterpret_cast<const T*>(p.theta) + (size_t)c * p.D;
+  T* logp = reinterpret_cast<T*>(p.logp);
+  T* grad = reinterpret_cast<T*>(p.grad);
+  const int KB = p.L.ks + 1, KA = p.L.ko + 1;
+  const bool prior = (p.flags & BL_FLAG_PRIOR) != 0;
+  if (q == 0) {
+    double lp = total + (add_const ? p.cop_const : 0.0);
+    if (prior) {
+      const double h2pi = 0.91893853320467274178;  // 0.5*log(2*pi)
+      for (int i = 0; i < KB; ++i) {
+        double z = ((double)theta[i] - p.prior_beta_loc) / p.prior_beta_scale;
+        lp += -0.5 * z * z - log(p.prior_beta_scale) - h2pi;
+      }
+      for (int i = 0; i < KA; ++i) {
+        double z = ((double)theta[KB + i] - p.prior_alpha_loc) / p.prior_alpha_scale;
+        lp += -0.5 * z * z - log(p.prior_alpha_scale) - h2pi;
+      }
+      for (int i = KB + KA; i < p.D; ++i) {
+        double x = (double)theta[i];
+        if (p.model == BL_MODEL_OCCU_COP) {  // occu_cop: Exponential(rate) on exp(x), + log|J| = x
+          lp += log(p.prior_fp_rate) - p.prior_fp_rate * exp(x) + x;
+        } else {               // Beta(a,b) on sigmoid(x), + log|J| = log c + log(1-c)
+          double a = p.prior_fp_a, b = p.prior_fp_b;
+          lp += a * log_sigmoid_d(x) + b * log_sigmoid_d(-x) + lgamma(a + b) - lgamma(a) - lgamma(b);
+        }
+      }
+    }
+    logp[c] = (T)lp;
+  } else {
+    const int i = q - 1;
+    double g = total;
+    if (prior) {
+      double x = (double)theta[i];
+      if (i < KB) g -= (x - p.prior_beta_loc) / (p.prior_beta_scale * p.prior_beta_scale);
+      else if (i < KB + KA) g -= (x - p.prior_alpha_loc) / (p.prior_alpha_scale * p.prior_alpha_scale);
+      else if (p.model == BL_MODEL_OCCU_COP) g += 1.0 - p.prior_fp_rate * exp(x);
+      else {
+        double c1 = 1.0 / (1.0 + exp(-x));
+        g += p.prior_fp_a * (1.0 - c1) - p.prior_fp_b * c1;
+      }
+    }
+    grad[(size_t)c * p.D + i] = (T)g;
+  }
+}
+
+// Stand-alone finalize (site-sharded mode: runs after the collective on the raw sums).
+template <typename T>
+__global__ void finalize_kernel(EvalParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.C * p.NQ) return;
+  finalize_chain<T>(p, idx / p.NQ, idx % p.NQ, p.sums[idx], false);
+}
+
+template <typename T, class Model, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  const int F = p.L.F;
+  const int WS = p.WS, WC = p.WC, NQ = p.NQ, D = p.D, DS = p.DS;
+  const uint32_t tile_elems = (uint32_t)WS * F * kWarp;        // one block-tile
+  const uint32_t tile_bytes = tile_elems * sizeof(T);
+  T* stage0 = reinterpret_cast<T*>(smem_raw + 128);
+  T* s_theta = stage0 + (size_t)p.nstage * tile_elems;
+  size_t theta_bytes = ((size_t)p.CB * DS * sizeof(T) + 15) & ~size_t(15);
+  double* s_acc = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_theta) + theta_bytes);
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ws = warp / WC, wc = warp % WC;
+  const int c0 = blockIdx.y * p.CB;
+  const int ncb = min(p.CB, p.C - c0);
+
+  // contiguous range of block-tiles for this site split
+  const int64_t nbt = p.n_block_tiles;
+  const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
+  const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
+  const int n_it = (int)(bt_end - bt_begin);
+  const T* packed = reinterpret_cast<const T*>(p.packed);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nstage; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < ncb * D; i += kBlockThreads)
+    s_theta[(i / D) * DS + (i % D)] = reinterpret_cast<const T*>(p.theta)[(size_t)c0 * D + i];
+  for (int i = tid; i < WS * p.CB * NQ; i += kBlockThreads) s_acc[i] = 0.0;
+  __syncthreads();
+  if constexpr (Model::kDerived > 0) {  // per-chain constants derived from theta, once per block
+    for (int ci = tid; ci < ncb; ci += kBlockThreads) Model::derive(p, s_theta + (size_t)ci * DS);
+    __syncthreads();
+  }
+
+  if (tid == 0) {
+    const int pre = min(p.nstage, n_it);
+    for (int s = 0; s < pre; ++s) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + s) * tile_elems, tile_bytes,
+                    &bars[s]);
+    }
+  }
+
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it % p.nstage;
+    mbar_wait(&bars[s], (uint32_t)((it / p.nstage) & 1));
+    const T* tile = stage0 + (size_t)s * tile_elems + (size_t)ws * F * kWarp;
+    const int64_t unit = ((bt_begin + it) * WS + ws) * kWarp + lane;
+    const bool valid = unit < p.L.n_units;
+
+    typename Model::Site site;
+    Model::load_site(p, tile, lane, site);
+
+    for (int ci = wc; ci < ncb; ci += WC) {
+      T q[Model::kNQMax];
+      Model::site_chain(p, tile, lane, site, s_theta + (size_t)ci * DS, q);
+      double* acc = s_acc + ((size_t)ws * p.CB + ci) * NQ;
+      if constexpr (Model::kNQMax <= 32) {
+        T mine = T(0);
+#pragma unroll
+        for (int i = 0; i < Model::kNQMax; ++i) {
+          T v = warp_sum(valid ? q[i] : T(0));
+          if (lane == i) mine = v;
+        }
+        if (lane < NQ) acc[lane] += (double)mine;
+      } else {
+        for (int i = 0; i < NQ; ++i) {
+          T v = warp_sum(valid ? q[i] : T(0));
+          if (lane == 0) acc[i] += (double)v;
+        }
+      }
+    }
+    __syncthreads();  // every warp is done reading stage s
+    if (tid == 0 && it + p.nstage < n_it) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + it + p.nstage) * tile_elems,
+                    tile_bytes, &bars[s]);
+    }
+  }
+  __syncthreads();
+
+  // block partial: sum the site-groups in fixed order, publish [bx][c][q]
+  double* my_partial = p.partial + ((size_t)blockIdx.x * p.C + c0) * NQ;
+  for (int i = tid; i < ncb * NQ; i += kBlockThreads) {
+    double v = 0.0;
+    for (int g = 0; g < WS; ++g) v += s_acc[(size_t)g * p.CB * NQ + i];
+    my_partial[i] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&p.counters[blockIdx.y], 1u);
+    s_is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  for (int i = tid; i < ncb * NQ; i += kBlockThreads) {
+    double total = 0.0;
+    const double* src = p.partial + (size_t)c0 * NQ + i;
+    for (unsigned int b = 0; b < gridDim.x; ++b) total += __ldcg(src + (size_t)b * p.C * NQ);
+    const int c = c0 + i / NQ, q = i % NQ;
+    if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
+    else finalize_chain<T>(p, c, q, total, true);
+  }
+  if (tid == 0) p.counters[blockIdx.y] = 0;  // self-reset for the next launch
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch geometry
+// ------------------------------------------------------------------------------------------
+struct Geometry {
+  int CB, n_chunks, WC, WS, nstage, nsplit;
+  int64_t n_block_tiles;
+  size_t smem_bytes;
+};
+
+inline int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
+
+inline size_t eval_smem_bytes(const Layout& L, int elem, int WS, int nstage, int CB, int D, int DS) {
+  size_t tile = (size_t)WS * L.F * kWarp * elem;
+  size_t theta = ((size_t)CB * DS * elem + 15) & ~size_t(15);
+  size_t acc = (size_t)WS * CB * (1 + D) * sizeof(double);
+  return 128 + nstage * tile + theta + acc;
+}
+
+inline Geometry plan_geometry(const Layout& L, int elem, int C, int D, int DS, int num_sms, int blocks_per_sm,
+                              size_t smem_limit) {
+  Geometry g{};
+  g.n_chunks = (C + kMaxChainsPerBlock - 1) / kMaxChainsPerBlock;
+  g.CB = (C + g.n_chunks - 1) / g.n_chunks;
+  g.WC = pow2_floor(g.CB < kWarpsPerBlock ? g.CB : kWarpsPerBlock);
+  g.WS = kWarpsPerBlock / g.WC;
+  g.n_block_tiles = (L.n_tiles + g.WS - 1) / g.WS;
+  g.nstage = kMaxStages;
+  while (g.nstage > 1 && eval_smem_bytes(L, elem, g.WS, g.nstage, g.CB, D, DS) > smem_limit / blocks_per_sm) --g.nstage;
+  g.smem_bytes = eval_smem_bytes(L, elem, g.WS, g.nstage, g.CB, D, DS);
+  int64_t want = (int64_t)num_sms * blocks_per_sm / g.n_chunks;
+  if (want < 1) want = 1;
+  g.nsplit = (int)(want < g.n_block_tiles ? want : g.n_block_tiles);
+  if (g.nsplit < 1) g.nsplit = 1;
+  return g;
+}
+
+}  // namespace bl

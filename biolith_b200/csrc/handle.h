@@ -1,0 +1,46 @@
+// The opaque dataset handle behind bl_dataset* (host side).
+#pragma once
+#include <atomic>
+#include <map>
+
+#include "engine.cuh"
+
+namespace bl {
+struct Plan {
+  Geometry g;
+  int occupancy;
+};
+}  // namespace bl
+
+struct bl_dataset {
+  bl_desc desc{};
+  bl::Layout L{};
+  int D = 0, n_extras = 0, DS = 0;
+  int num_sms = 0;
+  size_t smem_limit = 0;
+  void* packed = nullptr;
+  size_t packed_bytes = 0;
+  double cop_const = 0.0;
+  int64_t n_masked = 0;
+  // fp64 block partials [nsplit][C][NQ], per-chunk tickets, raw sums for the collective path
+  double* partial = nullptr;
+  size_t partial_cap = 0;
+  unsigned int* counters = nullptr;
+  size_t counters_cap = 0;
+  double* sums = nullptr;
+  size_t sums_cap = 0;
+  std::map<int, bl::Plan> plans;
+  // bl_eval_host staging
+  void *d_theta = nullptr, *d_out = nullptr, *h_theta = nullptr, *h_out = nullptr;
+  int host_cap = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // site-sharded collective (comm.cu)
+  void* comm = nullptr;
+};
+
+namespace bl {
+int fail(int code, const char* fmt, ...);
+int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce);
+extern std::atomic<int64_t> g_launches;
+}  // namespace bl

@@ -1,0 +1,177 @@
+"""GPU parity tests proper: the CUDA path through the C ABI vs the oracle / committed goldens.
+
+Tolerances (north star): fp32 -> 1e-5 relative on logp and on the gradient (relative to the
+gradient's scale); fp64 -> 1e-10.  Masks must be bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+IMPLEMENTED = {"occu"}
+RTOL = {"float32": 1e-5, "float64": 1e-10}
+
+
+def _make(g, dtype, prior=True, **kw):
+    import biolith_b200 as bb
+
+    d = g["data"]
+    mk = g["model_kwargs"]
+    return bb.OccupancyLikelihood(
+        g["model"], d["site_covs"], d["obs_covs"], d["obs"], d.get("session_duration"),
+        false_positives_constant=mk.get("fp_constant", False),
+        false_positives_unoccupied=mk.get("fp_unoccupied", False),
+        max_abundance=mk.get("max_abundance", 100), dtype=dtype, prior=prior, **kw)
+
+
+def assert_close(lp, gr, lp_ref, gr_ref, rtol, what=""):
+    lp, gr = np.asarray(lp, np.float64), np.asarray(gr, np.float64)
+    assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr)), what
+    rel = np.abs(lp - lp_ref) / np.maximum(np.abs(lp_ref), 1.0)
+    assert rel.max() <= rtol, f"{what} logp rel err {rel.max():.3e} > {rtol}"
+    scale = np.maximum(np.abs(gr_ref).max(axis=-1, keepdims=True), 1.0)
+    gerr = (np.abs(gr - gr_ref) / scale).max()
+    assert gerr <= rtol, f"{what} grad rel err {gerr:.3e} > {rtol}"
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_golden_parity(name, dtype):
+    g = load_golden(name)
+    if g["model"] not in IMPLEMENTED:
+        pytest.skip("model not built yet")
+    mode = "f32" if dtype == "float32" else "f64"
+    with _make(g, dtype) as lk:
+        assert lk.theta_dim == g["thetas"].shape[1]
+        lp, gr = lk.logp_and_grad(g["thetas"])
+        assert_close(lp, gr, g[f"logp_{mode}"], g[f"grad_{mode}"], RTOL[dtype], f"{name}/{dtype}")
+        assert np.array_equal(lk.mask(), g["mask"][0]), "NaN mask is not bit-exact"
+    with _make(g, dtype, prior=False) as lk:
+        lp, gr = lk.logp_and_grad(g["thetas"])
+        assert_close(lp, gr, g[f"loglik_{mode}"], g[f"gradlik_{mode}"], RTOL[dtype], f"{name}/{dtype}/lik")
+
+
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 5, 8, 31, 64, 257, 700])
+def test_chain_batching_is_consistent(n_chains):
+    """Every (C -> WS x WC arrangement, chunking) must give the same per-chain numbers."""
+    from oracle import occupancy as orc
+
+    g = load_golden("occu_5x3")
+    d = g["data"]
+    rng = np.random.default_rng(n_chains)
+    th = rng.uniform(-2, 2, size=(n_chains, 10))
+    pr = orc.prepare(d["site_covs"], d["obs_covs"], d["obs"])
+    ref_lp, ref_gr = orc.logp_grad("occu", th[: min(n_chains, 12)], pr)
+    with _make(g, "float32") as lk:
+        lp, gr = lk.logp_and_grad(th)
+        k = min(n_chains, 12)
+        assert_close(lp[:k], gr[:k], ref_lp, ref_gr, 1e-5, f"C={n_chains}")
+        # chain c of a batch == the same theta evaluated alone (bitwise: same reduction order)
+        lp1, gr1 = lk.logp_and_grad(th[-1])
+        np.testing.assert_allclose(lp1, lp[-1], rtol=2e-6)
+        np.testing.assert_allclose(gr1, gr[-1], rtol=2e-5, atol=2e-4)
+        # determinism: same call twice -> identical bits
+        lp2, gr2 = lk.logp_and_grad(th)
+        assert np.array_equal(lp, lp2) and np.array_equal(gr, gr2)
+
+
+@pytest.mark.parametrize("S,P,J,ks,ko", [(1, 1, 1, 1, 1), (33, 1, 5, 2, 1), (257, 1, 8, 5, 3), (40, 3, 4, 3, 2),
+                                         (1000, 1, 40, 1, 1), (64, 2, 33, 7, 9), (50, 1, 6, 0, 0)])
+@pytest.mark.parametrize("model", ["occu", "occu_rn", "occu_cop"])
+def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
+    import biolith_b200 as bb
+    from oracle import occupancy as orc
+
+    if model not in IMPLEMENTED:
+        pytest.skip("model not built yet")
+    rng = np.random.default_rng(S * 7 + J)
+    X = rng.normal(size=(S, ks))
+    W = rng.normal(size=(S, P, J, ko))
+    if model == "occu_cop":
+        y = rng.poisson(2.0, size=(1, S, P, J)).astype(float)
+    else:
+        y = (rng.uniform(size=(1, S, P, J)) < 0.35).astype(float)
+    # ragged visits: trailing replicates missing, plus NaNs in covariates
+    lens = rng.integers(0, J + 1, size=(S, P))
+    y[0][np.arange(J)[None, None, :] >= lens[:, :, None]] = np.nan
+    if ko:
+        W[rng.uniform(size=W.shape) < 0.03] = np.nan
+    if ks and S > 3:
+        X[rng.integers(0, S), rng.integers(0, ks)] = np.nan
+    T = rng.uniform(0.5, 9.0, size=(S, P, J)) if model == "occu_cop" else None
+    kw = dict(fp_constant=True) if model == "occu_cop" else (dict(max_abundance=30) if model == "occu_rn" else {})
+    D = ks + ko + 2 + (1 if model == "occu_cop" else 0)
+    th = rng.uniform(-1.5, 1.5, size=(6, D))
+    pr = orc.prepare(X, W, y, T)
+    ref_lp, ref_gr = orc.logp_grad(model, th, pr, **kw)
+    with bb.OccupancyLikelihood(model, X, W, y, T, false_positives_constant=(model == "occu_cop"),
+                                max_abundance=30) as lk:
+        lp, gr = lk.logp_and_grad(th)
+        assert_close(lp, gr, ref_lp, ref_gr, 1e-5, f"{model} S={S} P={P} J={J}")
+        assert np.array_equal(lk.mask(), orc.expected_mask(X, W, y)[0])
+
+
+def test_extreme_thetas_hit_the_clamps():
+    """|nu| beyond the clamp thresholds: values saturate at log(eps)/log(tiny), gradients vanish."""
+    from oracle import occupancy as orc
+
+    g = load_golden("occu_default")
+    d = g["data"]
+    th = np.array([[30.0, 5.0, 25.0, -9.0], [-40.0, 3.0, -30.0, 4.0], [100.0, 0.0, 100.0, 0.0],
+                   [-100.0, 0.0, -100.0, 0.0]])
+    pr = orc.prepare(d["site_covs"], d["obs_covs"], d["obs"])
+    ref_lp, ref_gr = orc.logp_grad("occu", th, pr)
+    with _make(g, "float32") as lk:
+        lp, gr = lk.logp_and_grad(th)
+        assert_close(lp, gr, ref_lp, ref_gr, 1e-5, "extreme")
+
+
+def test_rejects_non_binary_detections():
+    import biolith_b200 as bb
+
+    X = np.zeros((4, 1))
+    W = np.zeros((4, 1, 3, 1))
+    y = np.full((1, 4, 1, 3), 2.0)
+    with pytest.raises(bb.BiolithB200Error):
+        bb.OccupancyLikelihood("occu", X, W, y)
+
+
+def test_large_shape_properties():
+    """Config-2 shape (scaled to 200k sites to stay in seconds): size-independent properties.
+    (1) additivity over a site split: logp(A u B) - prior = loglik(A) + loglik(B);
+    (2) permutation invariance of sites; (3) masked observations do not change the result."""
+    import biolith_b200 as bb
+
+    rng = np.random.default_rng(5)
+    S, J, ks, ko = 200_000, 8, 5, 3
+    X = rng.normal(size=(S, ks)).astype(np.float32)
+    W = rng.normal(size=(S, 1, J, ko)).astype(np.float32)
+    y = (rng.uniform(size=(1, S, 1, J)) < 0.3).astype(np.float32)
+    th = rng.uniform(-1, 1, size=(16, 10))
+    kw = dict(prior=False)
+    with bb.OccupancyLikelihood("occu", X, W, y, **kw) as full:
+        lp, gr = full.logp_and_grad(th)
+    h = S // 3
+    with bb.OccupancyLikelihood("occu", X[:h], W[:h], y[:, :h], **kw) as a, \
+            bb.OccupancyLikelihood("occu", X[h:], W[h:], y[:, h:], **kw) as b:
+        la, ga = a.logp_and_grad(th)
+        lb, gb = b.logp_and_grad(th)
+    np.testing.assert_allclose(la.astype(np.float64) + lb, lp, rtol=2e-6)
+    np.testing.assert_allclose(ga.astype(np.float64) + gb, gr, rtol=1e-5, atol=1e-5 * np.abs(gr).max())
+    perm = rng.permutation(S)
+    with bb.OccupancyLikelihood("occu", X[perm], W[perm], y[:, perm], **kw) as pm:
+        lp2, gr2 = pm.logp_and_grad(th)
+    np.testing.assert_allclose(lp2, lp, rtol=2e-6)
+    np.testing.assert_allclose(gr2, gr, rtol=1e-5, atol=1e-5 * np.abs(gr).max())
+    # append fully-masked sites: nothing may change except exact zeros added
+    Xp = np.concatenate([X, np.full((1000, ks), np.nan, np.float32)])
+    Wp = np.concatenate([W, rng.normal(size=(1000, 1, J, ko)).astype(np.float32)])
+    yp = np.concatenate([y, np.ones((1, 1000, 1, J), np.float32)], axis=1)
+    with bb.OccupancyLikelihood("occu", Xp, Wp, yp, **kw) as pad:
+        lp3, gr3 = pad.logp_and_grad(th)
+        assert pad.n_masked == 1000 * J
+    # a fully masked site contributes logaddexp(log psi, log(1-psi)) = 0 up to rounding
+    np.testing.assert_allclose(lp3, lp, rtol=2e-6)
