@@ -226,7 +226,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
   if (e != cudaSuccess) { delete ds; return fail(BL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
   ds->num_sms = prop.multiProcessorCount;
-  ds->smem_limit = prop.sharedMemPerBlockOptin;
+  ds->smem_limit = prop.sharedMemPerBlockOptin - 1024;  // minus the kernels' static shared memory
 
   const Layout& L = ds->L;
   const size_t es = elem_size(d->dtype), ds_in = elem_size(d->data_dtype);

@@ -188,7 +188,7 @@ static cudaError_t launch_one(const EvalParams& p, dim3 grid, size_t smem, cudaS
   auto kern = eval_kernel<T, OccuModel<T, KS, KO, FP>, MINB>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
