@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- logp+grad evals/sec of the occupancy hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one batched evaluation of log-density + gradient for C chains over the whole
+synthetic dataset (what NUTS does at one leapfrog step of every chain).  Workload (N=1 default):
+BASELINE.json configs[1] -- occu, 5 site + 3 obs covariates, 1M sites x 8 visits, 1024 chains.
+For N>1 (torchrun, one rank per GPU) chains are sharded: every rank holds the dataset and its own
+1024 chains (weak scaling, no data-path collective); `--workload occu_sites16m` runs the
+site-sharded configs[4] (2M sites per rank, per-eval allreduce of the [C, 1+D] sums).
+
+Prints ONE JSON line (rank 0).  `value` = chain-evals/s with theta resident in HBM, CUDA-event
+timed per step on the launch stream; `e2e` = the same through the host-buffer C-ABI call
+(bl_eval_host: pinned H2D of theta, kernel, D2H of logp+grad every step); `roofline`,
+`cpu_baseline`, `clocks`, `gpu_launches` as the harness contract asks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, simulate kwargs, chains per GPU, shard mode)
+    "occu_1m_x8_c1024": ("occu", dict(n_site_covs=5, n_obs_covs=3, n_sites=1_000_000, deployment_days_per_site=56),
+                         1024, "chains"),
+    "occu_sites16m_c256": ("occu", dict(n_site_covs=5, n_obs_covs=3, n_sites=2_000_000, deployment_days_per_site=56),
+                           256, "sites"),
+    "occu_small": ("occu", dict(n_site_covs=5, n_obs_covs=3, n_sites=20_000, deployment_days_per_site=56), 256,
+                   "chains"),
+}
+METRIC = "logp+grad evals/sec (occu, 1M sites x 8 visits, chain-batched)"
+UNIT = "chain-evals/s"
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_data(workload, seed):
+    from biolith_b200.simulate import simulate_occupancy
+
+    model, kw, chains, shard = WORKLOADS[workload]
+    data, _ = simulate_occupancy(model, random_seed=seed, **kw)
+    X = data["site_covs"].astype(np.float32)   # the reference ingests as fp32 (utils/data.py:135-140)
+    W = data["obs_covs"].astype(np.float32)
+    y = data["obs"].astype(np.float32)
+    return model, X, W, y, chains, shard
+
+
+def run_reference(args, rank):
+    """CPU arm: the C/OpenMP restatement of the reference's path (the reference itself needs
+    jax+numpyro, which are neither installed nor installable on this image), all host threads."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+
+    model, X, W, y, chains, shard = make_data(args.workload, 0)
+    threads = c_oracle.max_threads()
+    D = X.shape[1] + W.shape[3] + 2
+    sample = args.cpu_chains
+    th = np.random.default_rng(1).uniform(-2, 2, size=(sample, D))
+    for _ in range(args.warmup):
+        c_oracle.occu_logp_grad(th[:1], X, W, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.occu_logp_grad(th, X, W, y)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sites": int(X.shape[0]), "visits": int(W.shape[2]),
+                   "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]),
+                   "note": "each step = %d chain-evals over the full dataset (bounded sample of the 1024-chain step)" % sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} chain-evals x {args.steps} steps, full 1M x 8 dataset, fp32, OpenMP {threads} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="occu_1m_x8_c1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
+    ap.add_argument("--cpu-chains", type=int, default=8, help="chain-evals per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import biolith_b200 as bb
+    from biolith_b200 import _lib
+
+    lib = _lib.load()
+    model, X, W, y, chains, shard = make_data(args.workload, 0 if shard_is_chains(args.workload) else rank)
+    if args.chains:
+        chains = args.chains
+    comm = None
+    lk = bb.OccupancyLikelihood(model, X, W, y, dtype=args.dtype, device=local_rank, max_chains=chains)
+    if shard == "sites" and world > 1:
+        from biolith_b200 import sharded
+
+        comm = sharded.attach_site_sharding(lk, dist, rank, world, local_rank, chains)
+    D = lk.theta_dim
+    npdt = lk.np_dtype
+    es = np.dtype(npdt).itemsize
+    # chain-sharded: every rank owns different chains; site-sharded: all ranks share the chains
+    th_seed = 1000 + (rank if shard == "chains" else 0)
+    theta = np.random.default_rng(th_seed).uniform(-2, 2, size=(chains, D)).astype(npdt)
+    stream = C.c_void_p()
+    _lib.check(lib.bl_stream_create(local_rank, C.byref(stream)), "bl_stream_create")
+    d_theta = bb.DeviceBuffer(theta.nbytes, local_rank)
+    d_logp = bb.DeviceBuffer(chains * es, local_rank)
+    d_grad = bb.DeviceBuffer(theta.nbytes, local_rank)
+    d_theta.upload(theta, stream)
+
+    def barrier():
+        _lib.check(lib.bl_stream_sync(stream), "sync")
+        if dist is not None:
+            dist.barrier()
+
+    def step_timed():
+        _lib.check(lib.bl_flush_l2(local_rank, stream), "flush")  # outside the per-step events
+        return lk.eval_timed(d_theta.ptr, chains, d_logp.ptr, d_grad.ptr, stream, iters=1)
+
+    for _ in range(args.warmup):
+        step_timed()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.bl_launch_count()
+    t_wall0 = time.perf_counter()
+    ms = [step_timed() for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.bl_launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = float(np.sum(ms))
+
+    # e2e: host buffers through the public call, H2D + D2H inside the timed region
+    for _ in range(2):
+        lk.logp_and_grad(theta)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lp_host, gr_host = lk.logp_and_grad(theta)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    if dist is not None:
+        import torch
+
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ln)
+        launches = int(ln[0])
+    chains_total = chains * (world if shard == "chains" else 1)
+    units_sites = X.shape[0] * (world if shard == "sites" else 1)
+    value = chains_total * args.steps / (total_ms * 1e-3)
+    e2e_value = chains_total * args.steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        alg_bytes = lk.algorithmic_bytes * chains  # C x B_eval per launch (per GPU)
+        ms_launch = total_ms / args.steps
+        achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "model": model, "sites": int(units_sites),
+                       "visits": int(W.shape[2]), "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]),
+                       "chains_per_gpu": chains, "chains_total": chains_total, "sharding": shard,
+                       "theta": "U(-2,2) per chain (init_to_uniform)",
+                       "l2": "flushed between timed steps (256 MB memset outside the per-step CUDA events); "
+                             "packed dataset %.0f MB" % (lk.packed_bytes / 1e6)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(theta.nbytes),
+                    "d2h_bytes_per_step": int(theta.nbytes + chains * es),
+                    "note": "bl_eval_host: pinned H2D theta + kernel + D2H logp,grad per step; dataset packed once per fit"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": PROFILED_TRAFFIC.get(args.workload),
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "note": "algorithmic bytes = C x B_eval (SURVEY 8d): every chain's density is a full pass "
+                                 "over the data; tile reuse across the chain batch makes the kernel FP32/SFU-issue "
+                                 "bound, so frac > 1 is expected (see DESIGN.md, profiles/)"},
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains)
+        print(json.dumps(line), flush=True)
+    lk.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def shard_is_chains(workload):
+    return WORKLOADS[workload][3] == "chains"
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the eval kernel (ncu --set full), by workload
+PROFILED_TRAFFIC = {}
+
+
+def cpu_baseline(X, W, y, D, sample):
+    from oracle import c_oracle
+
+    threads = c_oracle.max_threads()
+    th = np.random.default_rng(1).uniform(-2, 2, size=(sample, D))
+    c_oracle.occu_logp_grad(th[:1], X, W, y)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 or (time.perf_counter() - t0 < 2.0 and reps < 50):
+        c_oracle.occu_logp_grad(th, X, W, y)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample * reps} chain-evals of the full dataset ({X.shape[0]} sites), fp32 C/OpenMP "
+                      f"restatement (oracle/occu_oracle.c), {threads} threads, {dt:.1f} s wall"}
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,10 @@ int occu_derived_slots(uint32_t flags);
 int occu_rn_derived_slots(uint32_t flags);
 int occu_cop_derived_slots(uint32_t flags);
 size_t occu_rn_extra_smem(const Layout& L, int K, int elem);
+bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
+cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
+
+constexpr int kChainKernelMinChains = 64;
 
 static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st,
                                 int* occ) {
@@ -79,13 +83,22 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     if (ds->desc.model == BL_MODEL_OCCU_RN) extra = occu_rn_extra_smem(ds->L, ds->desc.max_abundance, elem);
     pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit - 2 * extra);
     pl.g.smem_bytes += extra;
+    pl.chain_kernel = ds->desc.model == BL_MODEL_OCCU && C >= kChainKernelMinChains && !ds->force_engine &&
+                      occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags);
+    if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
+      pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
+      pl.g.n_block_tiles = ds->L.n_tiles;
+      pl.g.nstage = kMaxStages;
+      pl.g.smem_bytes = 128 + (size_t)pl.g.nstage * ds->L.F * kWarp * elem;
+    }
     if (pl.g.smem_bytes > ds->smem_limit)
       return fail(BL_ERR_UNSUPPORTED, "shape needs %zu B of shared memory per block (> %zu)", pl.g.smem_bytes,
                   ds->smem_limit);
     EvalParams p;
     fill_params(ds, p);
     int occ = 0;
-    cudaError_t e = launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
+    cudaError_t e = pl.chain_kernel ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                                    : launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
     if (e != cudaSuccess) return fail(BL_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (occ < 1) return fail(BL_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", pl.g.smem_bytes);
     pl.occupancy = occ;
@@ -144,7 +157,9 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.nstage = pl->g.nstage;
   p.nsplit = pl->g.nsplit;
   p.n_block_tiles = pl->g.n_block_tiles;
-  cudaError_t e = launch_model(ds, p, dim3(pl->g.nsplit, pl->g.n_chunks), pl->g.smem_bytes, st, nullptr);
+  const dim3 grid(pl->g.nsplit, pl->g.n_chunks);
+  cudaError_t e = pl->chain_kernel ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
+                                   : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
   if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return BL_OK;

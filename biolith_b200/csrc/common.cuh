@@ -28,7 +28,8 @@ constexpr int kMaxStages = 4;
 //   tile t occupies F * 32 elements:  field f of lane l at  t*F*32 + f*32 + l     ("SoA in tile")
 //   fields:  [0, Ks)                 X_k               (NaN -> 0, +-inf -> +-max)
 //            [Ks, Ks + J*Ko)         W_{j,k} at Ks + j*Ko + k
-//            occu / occu_rn:  NW = ceil(J/32) words of y bits, then NW words of mask bits
+//            occu / occu_rn:  NW = ceil(J/32) words of y bits, NW words of mask bits, then n1 = number of
+//                             unmasked detections as a float (data-only; z=0 branch / k=0 state)
 //            occu_cop:        J floats y (0 if masked), J floats T (0 if masked), Sy, ST, NW mask words
 //   every warp-wide read of one field is one coalesced 128-byte (fp32) line, and a whole tile is a
 //   contiguous, 16-byte aligned chunk -> one cp.async.bulk (TMA) per block-tile.
@@ -42,6 +43,7 @@ struct Layout {
   int off_m;       // mask bit words
   int off_t;       // cop: T floats
   int off_sy;      // cop: sum of masked y; +1 = sum of masked T
+  int off_n1;      // occu/rn: float count of unmasked detections
   int64_t n_units; // S*P
   int64_t n_tiles; // ceil(n_units/32)
   int64_t n_tiles_padded;  // multiple of kWarpsPerBlock so any block-tile TMA stays in bounds
@@ -58,9 +60,11 @@ inline Layout make_layout(int model, int64_t S, int P, int J, int ks, int ko) {
     L.off_t = f; f += J;
     L.off_sy = f; f += 2;
     L.off_m = f; f += L.nw;
+    L.off_n1 = -1;
   } else {
     L.off_y = f; f += L.nw;
     L.off_m = f; f += L.nw;
+    L.off_n1 = f; f += 1;
     L.off_t = -1; L.off_sy = -1;
   }
   L.F = f;
@@ -143,6 +147,44 @@ __device__ __forceinline__ LogSig<T> log_sigmoid_pair(T x) {
   r.l1mp = lo ? N::neg_tiny() : (hi ? N::log_eps() : l1);
   return r;
 }
+
+// ------------------------------------------------------------------------------------------
+// Bounded-error SFU math (fp32).  NOT -use_fast_math: three explicitly chosen MUFU approximations
+// whose errors are *absolute* and below the fp32 rounding already present in the sums they feed
+// (DESIGN.md "numerics"): ex2.approx (rel 2^-22), lg2.approx on (1,2] (abs 2^-22), rcp.approx on
+// (1,2] (rel 2^-23).  softsig() returns softplus / sigmoid of the CLAMPED argument: clamping x to
+// [log tiny, log((1-eps)/eps)] reproduces numpyro's clamp_probs values exactly (log p~ = xc - s,
+// log1p(-p~) = -s) and `inr` carries its zero-derivative region.
+// ------------------------------------------------------------------------------------------
+namespace sfu {
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kXHi = 15.9423847f;     // log((1-eps)/eps): p~ hits 1-eps
+constexpr float kXLo = -87.33654475f;   // log(tiny):        p~ hits tiny
+
+struct SoftSig {
+  float xc;   // clamped argument
+  float s;    // softplus(xc)  = -log1p(-p~)
+  float p;    // sigmoid(xc)
+  bool inr;   // x inside the clamp range (derivative not zeroed)
+};
+
+template <bool CLAMP>
+__device__ __forceinline__ SoftSig softsig(float x) {
+  SoftSig r;
+  r.xc = CLAMP ? fminf(fmaxf(x, kXLo), kXHi) : x;
+  r.inr = CLAMP ? (r.xc == x) : true;
+  const float t = ex2(-fabsf(r.xc) * kLog2e);   // e^{-|x|} in (0,1]
+  const float u = 1.0f + t;
+  const float inv = rcp(u);
+  r.s = fmaf(lg2(u), kLn2, fmaxf(r.xc, 0.0f));
+  r.p = (r.xc >= 0.0f) ? inv : t * inv;
+  return r;
+}
+}  // namespace sfu
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

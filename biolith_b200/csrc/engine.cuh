@@ -76,6 +76,31 @@ __global__ void finalize_kernel(EvalParams p) {
   finalize_chain<T>(p, idx / p.NQ, idx % p.NQ, p.sums[idx], false);
 }
 
+// Called by every thread of a block after it has published its [bx][c][q] partials: the last block
+// of the chain chunk (ticket counter) sums the site splits in split order and writes the outputs.
+template <typename T>
+__device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int ncb, int* s_is_last) {
+  const int tid = threadIdx.x, NQ = p.NQ;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&p.counters[blockIdx.y], 1u);
+    *s_is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!*s_is_last) return;
+  __threadfence();
+  for (int i = tid; i < ncb * NQ; i += blockDim.x) {
+    double total = 0.0;
+    const double* src = p.partial + (size_t)c0 * NQ + i;
+    for (unsigned int b = 0; b < gridDim.x; ++b) total += __ldcg(src + (size_t)b * p.C * NQ);
+    const int c = c0 + i / NQ, q = i % NQ;
+    if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
+    else finalize_chain<T>(p, c, q, total, true);
+  }
+  if (tid == 0) p.counters[blockIdx.y] = 0;  // self-reset for the next launch
+}
+
 template <typename T, class Model, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -169,24 +194,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalPar
     for (int g = 0; g < WS; ++g) v += s_acc[(size_t)g * p.CB * NQ + i];
     my_partial[i] = v;
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int ticket = atomicAdd(&p.counters[blockIdx.y], 1u);
-    s_is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-  for (int i = tid; i < ncb * NQ; i += kBlockThreads) {
-    double total = 0.0;
-    const double* src = p.partial + (size_t)c0 * NQ + i;
-    for (unsigned int b = 0; b < gridDim.x; ++b) total += __ldcg(src + (size_t)b * p.C * NQ);
-    const int c = c0 + i / NQ, q = i % NQ;
-    if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
-    else finalize_chain<T>(p, c, q, total, true);
-  }
-  if (tid == 0) p.counters[blockIdx.y] = 0;  // self-reset for the next launch
+  finish_block<T>(p, c0, ncb, &s_is_last);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@ namespace bl {
 struct Plan {
   Geometry g;
   int occupancy;
+  bool chain_kernel;  // lane = chain variant (occu_chain.cu) instead of the site-parallel engine
 };
 }  // namespace bl
 
@@ -30,6 +31,7 @@ struct bl_dataset {
   double* sums = nullptr;
   size_t sums_cap = 0;
   std::map<int, bl::Plan> plans;
+  bool force_engine = false;  // BL_FLAG_STRICT_MATH: always use the site-parallel libm-accurate engine
   // bl_eval_host staging
   void *d_theta = nullptr, *d_out = nullptr, *h_theta = nullptr, *h_out = nullptr;
   int host_cap = 0;

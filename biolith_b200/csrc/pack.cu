@@ -39,6 +39,7 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
     base[k * kWarp] = nan_to_num<TO>(v);
   }
   uint32_t yw = 0, mw = 0;
+  int n1 = 0;
   TO sy = TO(0), st = TO(0);
   unsigned long long masked = 0;
   for (int j = 0; j < J; ++j) {
@@ -60,7 +61,7 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
       if (m) { sy += yv; st += tv; }
     } else {
       if (m) {
-        if (yv == TO(1)) yw |= 1u << (j & 31);
+        if (yv == TO(1)) { yw |= 1u << (j & 31); ++n1; }
         else if (yv != TO(0)) atomicOr(err_flag, 1);  // detections must be binary
       }
     }
@@ -73,6 +74,8 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
   if (model == BL_MODEL_OCCU_COP) {
     base[L.off_sy * kWarp] = sy;
     base[(L.off_sy + 1) * kWarp] = st;
+  } else {
+    base[L.off_n1 * kWarp] = (TO)n1;
   }
   if (masked) atomicAdd(n_masked, masked);
 }

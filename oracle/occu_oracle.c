@@ -1,0 +1,144 @@
+/*
+ * CPU restatement (plain C + OpenMP) of the occupancy log-density + gradient.
+ *
+ * TEST INFRASTRUCTURE ONLY: linked/loaded only by tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py.  Never part of the product path.
+ * PARITY STATUS: unpinned against numpyro (see oracle/occupancy.py header); this file is pinned
+ * to oracle/occupancy.py (tests/test_oracle_c.py) which is pinned to the golden fixtures.
+ *
+ * Restates, for the `occu` model without false positives (the BASELINE.json metric config):
+ *   biolith/models/occu.py:136-142   NaN mask + nan_to_num            (done on the fly per visit)
+ *   biolith/regression/linear.py:59-66  eta = b0 + X.b, nu = a0 + W.a
+ *   biolith/models/occu.py:207-242   psi, p, masked Bernoulli log-prob, enumeration over z
+ *   numpyro clamp_probs / BernoulliProbs.log_prob semantics (tiny / 1-eps clamps, zero slope outside)
+ *   reverse-mode gradient (hand-derived; SURVEY.md section 8a closed forms)
+ * Arithmetic type = `real` (float or double, chosen per call), reductions in double.
+ */
+#include <float.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXK 16
+
+#define DEFINE_ORACLE(NAME, real, EXP, LOG1P, FABS, LOG_TINY, LOG_EPS, LOG1M_EPS, NEG_TINY, RMAX)                   \
+  static inline real NAME##_n2n(real v) { return isnan(v) ? (real)0 : (isinf(v) ? (v > 0 ? RMAX : -RMAX) : v); }   \
+  static inline void NAME##_lsp(real x, real* p, real* q, real* lp, real* l1, int* inr) {                          \
+    real t = EXP(-FABS(x)), l = LOG1P(t), inv = (real)1 / ((real)1 + t), ti = t * inv;                              \
+    *p = x >= 0 ? inv : ti;                                                                                         \
+    *q = x >= 0 ? ti : inv;                                                                                         \
+    real a = (x < 0 ? x : 0) - l, b = -(x > 0 ? x : 0) - l;                                                         \
+    int lo = a <= (real)LOG_TINY, hi = b <= (real)LOG_EPS;                                                          \
+    *inr = !(lo || hi);                                                                                             \
+    *lp = lo ? (real)LOG_TINY : (hi ? (real)LOG1M_EPS : a);                                                         \
+    *l1 = lo ? (real)NEG_TINY : (hi ? (real)LOG_EPS : b);                                                           \
+  }                                                                                                                 \
+  static void NAME(long S, int P, int J, int Ks, int Ko, const real* y, const real* X, const real* W,              \
+                   const double* theta, int C, int prior, double* logp, double* grad) {                             \
+    const int D = Ks + Ko + 2, NQ = D + 1;                                                                          \
+    const long U = S * (long)P;                                                                                     \
+    for (int c = 0; c < C; ++c) {                                                                                   \
+      real b[MAXK + 1], a[MAXK + 1];                                                                                \
+      for (int k = 0; k <= Ks; ++k) b[k] = (real)theta[(size_t)c * D + k];                                          \
+      for (int k = 0; k <= Ko; ++k) a[k] = (real)theta[(size_t)c * D + Ks + 1 + k];                                 \
+      double acc[2 * MAXK + 3];                                                                                     \
+      memset(acc, 0, sizeof(acc));                                                                                  \
+      _Pragma("omp parallel")                                                                                       \
+      {                                                                                                             \
+        double loc[2 * MAXK + 3];                                                                                   \
+        memset(loc, 0, sizeof(loc));                                                                                \
+        _Pragma("omp for schedule(static)")                                                                         \
+        for (long u = 0; u < U; ++u) {                                                                              \
+          const long s = u / P;                                                                                     \
+          int site_nan = 0;                                                                                         \
+          real x[MAXK], eta = b[0];                                                                                 \
+          for (int k = 0; k < Ks; ++k) {                                                                            \
+            real v = X[s * Ks + k];                                                                                 \
+            site_nan |= isnan(v);                                                                                   \
+            x[k] = NAME##_n2n(v);                                                                                   \
+            eta += x[k] * b[k + 1];                                                                                 \
+          }                                                                                                         \
+          real L1 = 0, ga[MAXK + 1];                                                                                \
+          for (int k = 0; k <= Ko; ++k) ga[k] = 0;                                                                  \
+          int n1 = 0, n0 = 0;                                                                                       \
+          for (int j = 0; j < J; ++j) {                                                                             \
+            const real* w = W + ((size_t)u * J + j) * Ko;                                                           \
+            real wv[MAXK], nu = a[0];                                                                               \
+            int cov_nan = site_nan;                                                                                 \
+            for (int k = 0; k < Ko; ++k) {                                                                          \
+              cov_nan |= isnan(w[k]);                                                                               \
+              wv[k] = NAME##_n2n(w[k]);                                                                             \
+              nu += wv[k] * a[k + 1];                                                                               \
+            }                                                                                                       \
+            const real yv = y[(size_t)u * J + j];                                                                   \
+            if (cov_nan || !isfinite(yv)) continue; /* mask_missing_obs */                                          \
+            real p, q, lp, l1;                                                                                      \
+            int inr;                                                                                                \
+            NAME##_lsp(nu, &p, &q, &lp, &l1, &inr);                                                                 \
+            const int yb = yv != 0;                                                                                 \
+            n1 += yb;                                                                                               \
+            n0 += !yb;                                                                                              \
+            L1 += yb ? lp : l1;                                                                                     \
+            const real g = inr ? (yb ? q : -p) : 0;                                                                 \
+            ga[0] += g;                                                                                             \
+            for (int k = 0; k < Ko; ++k) ga[k + 1] += g * wv[k];                                                    \
+          }                                                                                                         \
+          const real L0 = (real)n1 * (real)LOG_TINY + (real)n0 * (real)NEG_TINY;                                    \
+          real psi, qpsi, lpsi, l1psi;                                                                              \
+          int in_psi;                                                                                               \
+          NAME##_lsp(eta, &psi, &qpsi, &lpsi, &l1psi, &in_psi);                                                     \
+          const real av = lpsi + L1, bv = l1psi + L0, dd = av - bv;                                                 \
+          const real td = EXP(-FABS(dd)), inv = (real)1 / ((real)1 + td);                                           \
+          const real r = dd >= 0 ? inv : td * inv;                                                                  \
+          const real ell = (av > bv ? av : bv) + LOG1P(td);                                                         \
+          const real geta = in_psi ? r - psi : 0;                                                                   \
+          loc[0] += ell;                                                                                            \
+          loc[1] += geta;                                                                                           \
+          for (int k = 0; k < Ks; ++k) loc[2 + k] += geta * x[k];                                                   \
+          for (int k = 0; k <= Ko; ++k) loc[2 + Ks + k] += r * ga[k];                                               \
+        }                                                                                                           \
+        _Pragma("omp critical")                                                                                     \
+        for (int i = 0; i < NQ; ++i) acc[i] += loc[i];                                                              \
+      }                                                                                                             \
+      double lp = acc[0];                                                                                           \
+      for (int i = 0; i < D; ++i) {                                                                                 \
+        double g = acc[1 + i], t = theta[(size_t)c * D + i];                                                        \
+        if (prior) {                                                                                                \
+          lp += -0.5 * t * t - 0.91893853320467274178;                                                              \
+          g -= t;                                                                                                   \
+        }                                                                                                           \
+        grad[(size_t)c * D + i] = g;                                                                                \
+      }                                                                                                             \
+      logp[c] = lp;                                                                                                 \
+    }                                                                                                               \
+  }
+
+DEFINE_ORACLE(occu_f32, float, expf, log1pf, fabsf, -87.33654475f, -15.9423851f, -1.19209297e-07f, -FLT_MIN, FLT_MAX)
+DEFINE_ORACLE(occu_f64, double, exp, log1p, fabs, -708.3964185322641, -36.04365338911715, -2.2204460492503136e-16,
+              -DBL_MIN, DBL_MAX)
+
+/* dtype: 0 = float arithmetic on float arrays, 1 = double on double arrays.  theta/logp/grad double.
+ * Arrays in the reference layout: y (1,S,P,J), X (S,Ks), W (S,P,J,Ko), C-contiguous. */
+int oracle_occu_logp_grad(int dtype, long S, int P, int J, int Ks, int Ko, const void* y, const void* X,
+                          const void* W, const double* theta, int C, int prior, int nthreads, double* logp,
+                          double* grad) {
+  if (Ks > MAXK || Ko > MAXK) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  if (dtype == 0) occu_f32(S, P, J, Ks, Ko, (const float*)y, (const float*)X, (const float*)W, theta, C, prior, logp, grad);
+  else occu_f64(S, P, J, Ks, Ko, (const double*)y, (const double*)X, (const double*)W, theta, C, prior, logp, grad);
+  return 0;
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -175,3 +175,29 @@ def test_large_shape_properties():
         assert pad.n_masked == 1000 * J
     # a fully masked site contributes logaddexp(log psi, log(1-psi)) = 0 up to rounding
     np.testing.assert_allclose(lp3, lp, rtol=2e-6)
+
+
+def test_config2_full_size_against_c_oracle():
+    """BASELINE.json configs[1] at full size: 1M sites x 8 visits, 5+3 covariates, 1024 chains.
+    A sample of chains is checked against the fp64 C/OpenMP oracle; plus the checksum property
+    sum_c logp_c is reproduced when the chains are evaluated in a different batch split."""
+    import biolith_b200 as bb
+    from biolith_b200.simulate import simulate_occupancy
+    from oracle import c_oracle
+
+    data, _ = simulate_occupancy("occu", n_site_covs=5, n_obs_covs=3, n_sites=1_000_000,
+                                 deployment_days_per_site=56, random_seed=0)
+    X = data["site_covs"].astype(np.float32)
+    W = data["obs_covs"].astype(np.float32)
+    y = data["obs"].astype(np.float32)
+    th = np.random.default_rng(3).uniform(-2, 2, size=(1024, 10)).astype(np.float32)
+    with bb.OccupancyLikelihood("occu", X, W, y, max_chains=1024) as lk:
+        lp, gr = lk.logp_and_grad(th)
+        idx = [0, 1, 255, 256, 700, 1023]
+        ref_lp, ref_gr = c_oracle.occu_logp_grad(th[idx].astype(np.float64), X.astype(np.float64),
+                                                 W.astype(np.float64), y.astype(np.float64), dtype=np.float64)
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, "config2 full size")
+        lp_a, gr_a = lk.logp_and_grad(th[:300])   # different chunking (2 x 150 chains)
+        lp_b, gr_b = lk.logp_and_grad(th[300:])
+        np.testing.assert_allclose(np.concatenate([lp_a, lp_b]), lp, rtol=1e-6)
+        np.testing.assert_allclose(np.concatenate([gr_a, gr_b]), gr, rtol=1e-5, atol=1e-5 * np.abs(gr).max())
