@@ -39,6 +39,7 @@ int occu_cop_derived_slots(uint32_t flags);
 size_t occu_rn_extra_smem(const Layout& L, int K, int elem);
 bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
+size_t occu_chain_smem(const Layout& L, int nstage);
 
 constexpr int kChainKernelMinChains = 64;
 
@@ -81,15 +82,25 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     const int elem = (int)elem_size(ds->desc.dtype);
     size_t extra = 0;
     if (ds->desc.model == BL_MODEL_OCCU_RN) extra = occu_rn_extra_smem(ds->L, ds->desc.max_abundance, elem);
-    pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit - 2 * extra);
-    pl.g.smem_bytes += extra;
+    pl.rn_global = false;
+    if (extra && extra + 4096 < ds->smem_limit) {
+      // the per-thread A_k column goes to shared memory when it fits beside the tile ring ...
+      pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 1, ds->smem_limit - extra);
+      if (pl.g.smem_bytes + extra + 128 > ds->smem_limit) pl.rn_global = true;
+    } else if (extra) {
+      pl.rn_global = true;
+    }
+    if (pl.rn_global) extra = 0;  // ... else to (coalesced, L2-resident) global scratch
+    if (!extra) pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit);
+    pl.rn_scratch_off = (uint32_t)((pl.g.smem_bytes + 127) & ~size_t(127));
+    pl.g.smem_bytes = pl.rn_scratch_off + extra;
     pl.chain_kernel = ds->desc.model == BL_MODEL_OCCU && C >= kChainKernelMinChains && !ds->force_engine &&
                       occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags);
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
       pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
       pl.g.n_block_tiles = ds->L.n_tiles;
       pl.g.nstage = kMaxStages;
-      pl.g.smem_bytes = 128 + (size_t)pl.g.nstage * ds->L.F * kWarp * elem;
+      pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage);
     }
     if (pl.g.smem_bytes > ds->smem_limit)
       return fail(BL_ERR_UNSUPPORTED, "shape needs %zu B of shared memory per block (> %zu)", pl.g.smem_bytes,
@@ -110,7 +121,11 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
   }
   Plan& pl = it->second;
   const size_t need = (size_t)pl.g.nsplit * C * (1 + ds->D);
-  if (need > ds->partial_cap || (size_t)pl.g.n_chunks > ds->counters_cap || (size_t)C > ds->sums_cap) {
+  const size_t rn_need = pl.rn_global ? (size_t)(ds->desc.max_abundance + 1) * pl.g.nsplit * pl.g.n_chunks *
+                                            kBlockThreads * elem_size(ds->desc.dtype)
+                                      : 0;
+  if (need > ds->partial_cap || (size_t)pl.g.n_chunks > ds->counters_cap || (size_t)C > ds->sums_cap ||
+      rn_need > ds->rn_scratch_cap) {
     // (re)allocation synchronises; callers that must not sync pass desc.max_chains up front
     cudaDeviceSynchronize();
     if (need > ds->partial_cap) {
@@ -125,6 +140,11 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       if (cudaMalloc(&ds->counters, n * sizeof(unsigned int)) != cudaSuccess) return fail(BL_ERR_NOMEM, "counters");
       cudaMemset(ds->counters, 0, n * sizeof(unsigned int));
       ds->counters_cap = n;
+    }
+    if (rn_need > ds->rn_scratch_cap) {
+      cudaFree(ds->rn_scratch);
+      if (cudaMalloc(&ds->rn_scratch, rn_need) != cudaSuccess) return fail(BL_ERR_NOMEM, "occu_rn scratch (%zu B)", rn_need);
+      ds->rn_scratch_cap = rn_need;
     }
     if ((size_t)C > ds->sums_cap) {
       cudaFree(ds->sums);
@@ -157,6 +177,8 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.nstage = pl->g.nstage;
   p.nsplit = pl->g.nsplit;
   p.n_block_tiles = pl->g.n_block_tiles;
+  p.rn_scratch_off = pl->rn_scratch_off;
+  p.rn_scratch_global = pl->rn_global ? ds->rn_scratch : nullptr;
   const dim3 grid(pl->g.nsplit, pl->g.n_chunks);
   cudaError_t e = pl->chain_kernel ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                                    : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
@@ -231,6 +253,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   bl_dataset* ds = new (std::nothrow) bl_dataset();
   if (!ds) return fail(BL_ERR_NOMEM, "host allocation failed");
   ds->desc = *d;
+  ds->force_engine = (d->flags & BL_FLAG_STRICT_MATH) != 0;
   ds->L = make_layout(d->model, d->n_sites, d->n_periods, d->n_replicates, d->n_site_covs, d->n_obs_covs);
   ds->n_extras = (fpc ? 1 : 0) + (fpu ? 1 : 0);
   ds->D = d->n_site_covs + 1 + d->n_obs_covs + 1 + ds->n_extras;
@@ -331,6 +354,7 @@ int bl_dataset_destroy(bl_dataset* ds) {
   if (!ds) return BL_OK;
   cudaSetDevice(ds->desc.device);
   cudaFree(ds->packed); cudaFree(ds->partial); cudaFree(ds->counters); cudaFree(ds->sums);
+  cudaFree(ds->rn_scratch);
   cudaFree(ds->d_theta); cudaFree(ds->d_out);
   if (ds->h_theta) cudaFreeHost(ds->h_theta);
   if (ds->h_out) cudaFreeHost(ds->h_out);

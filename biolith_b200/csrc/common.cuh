@@ -186,6 +186,30 @@ __device__ __forceinline__ SoftSig softsig(float x) {
 }
 }  // namespace sfu
 
+// Scalar math selected by (type, SFU): SFU forms are only ever instantiated for float.
+template <typename T, bool SFU> struct Mth {
+  static __device__ __forceinline__ T exp_(T x) { return Num<T>::exp_(x); }
+  static __device__ __forceinline__ T log_(T x) { return Num<T>::log_(x); }
+  static __device__ __forceinline__ T rcp_(T x) { return T(1) / x; }
+  // softplus(x) and sigmoid(x), libm-accurate
+  static __device__ __forceinline__ void softsig(T x, T& s, T& p) {
+    const T t = Num<T>::exp_(-Num<T>::abs_(x));
+    const T inv = T(1) / (T(1) + t);
+    s = Num<T>::max_(x, T(0)) + Num<T>::log1p_(t);
+    p = x >= T(0) ? inv : t * inv;
+  }
+};
+template <> struct Mth<float, true> {
+  static __device__ __forceinline__ float exp_(float x) { return sfu::ex2(x * sfu::kLog2e); }
+  static __device__ __forceinline__ float log_(float x) { return sfu::lg2(x) * sfu::kLn2; }
+  static __device__ __forceinline__ float rcp_(float x) { return sfu::rcp(x); }
+  static __device__ __forceinline__ void softsig(float x, float& s, float& p) {
+    const sfu::SoftSig r = sfu::softsig<false>(x);
+    s = r.s;
+    p = r.p;
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -255,6 +279,8 @@ struct EvalParams {
   int64_t n_block_tiles;  // ceil(n_tiles / WS)
   uint32_t flags;
   int K;        // occu_rn: max_abundance
+  uint32_t rn_scratch_off;  // occu_rn: byte offset of the per-thread A_k scratch in dynamic smem
+  void* rn_scratch_global;  // occu_rn: non-NULL -> A_k scratch in global memory (too big for smem)
   double cop_const;  // occu_cop: sum_s sum_j m (y log T - lgamma(y+1)), data-only
   double prior_beta_loc, prior_beta_scale, prior_alpha_loc, prior_alpha_scale;
   double prior_fp_a, prior_fp_b, prior_fp_rate;

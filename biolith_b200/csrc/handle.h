@@ -9,6 +9,8 @@ namespace bl {
 struct Plan {
   Geometry g;
   int occupancy;
+  uint32_t rn_scratch_off;
+  bool rn_global;  // occu_rn A_k scratch lives in global memory
   bool chain_kernel;  // lane = chain variant (occu_chain.cu) instead of the site-parallel engine
 };
 }  // namespace bl
@@ -30,6 +32,8 @@ struct bl_dataset {
   size_t counters_cap = 0;
   double* sums = nullptr;
   size_t sums_cap = 0;
+  void* rn_scratch = nullptr;  // occu_rn global A_k scratch (only when it does not fit in smem)
+  size_t rn_scratch_cap = 0;
   std::map<int, bl::Plan> plans;
   bool force_engine = false;  // BL_FLAG_STRICT_MATH: always use the site-parallel libm-accurate engine
   // bl_eval_host staging

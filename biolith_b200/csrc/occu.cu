@@ -9,14 +9,18 @@
 //   r  = P(z=1 | y) = sigmoid(a - b);  dl/deta = r - psi;  dl/dnu_j = r m_j (y_j - p_j)
 // with numpyro's clamp_probs semantics (zero derivative outside [tiny, 1-eps]) decided in log space.
 // The closed form is oracle/occupancy.py:occu_logp_grad; parity tests compare against it.
+#include <type_traits>
+
 #include "engine.cuh"
 
 namespace bl {
 
 // FP = a false-positive flag is set (exactly one extra parameter: logit c or logit u)
-template <typename T, int KS, int KO, bool FP>
+template <typename T, int KS, int KO, bool FP, bool STRICT>
 struct OccuModel {
   using N = Num<T>;
+  // bounded-error SFU math for fp32 unless BL_FLAG_STRICT_MATH (fp64 is always libm)
+  static constexpr bool kSfu = std::is_same<T, float>::value && !STRICT && !FP;
   static constexpr bool kGeneric = (KS < 0);
   static constexpr int KSM = kGeneric ? kMaxCov : KS;
   static constexpr int KOM = kGeneric ? kMaxCov : KO;
@@ -112,7 +116,12 @@ struct OccuModel {
         }
       }
       T term, g;
-      if constexpr (!FP) {
+      if constexpr (kSfu) {
+        const sfu::SoftSig ss = sfu::softsig<true>(nu);
+        const float yf = y ? 1.f : 0.f;
+        term = fmaf(yf, ss.xc, -ss.s);
+        g = ss.inr ? (yf - ss.p) : 0.f;
+      } else if constexpr (!FP) {
         const LogSig<T> ls = log_sigmoid_pair<T>(nu);
         term = y ? ls.lp : ls.l1mp;
         g = ls.inr ? (y ? ls.q : -ls.p) : T(0);
@@ -154,15 +163,29 @@ struct OccuModel {
       L0 = N::fma_(s.n1, d[1], s.n0 * d[2]);
       dL0 = s.n1 * d[3] - s.n0 * d[4];  // dL0/dP0 (zero when P0 is clipped)
     }
-    const LogSig<T> se = log_sigmoid_pair<T>(eta);
-    const T av = se.lp + L1;
-    const T bv = se.l1mp + L0;
-    const T dd = av - bv;
-    const T td = N::exp_(-N::abs_(dd));
-    const T inv = N::rcp_(T(1) + td);
-    const T r = (dd >= T(0)) ? inv : td * inv;
-    const T ell = N::max_(av, bv) + N::log1p_(td);
-    const T geta = se.inr ? (r - se.p) : T(0);
+    T ell, r, geta;
+    if constexpr (kSfu) {
+      const sfu::SoftSig se = sfu::softsig<true>(eta);
+      const float av = (se.xc - se.s) + L1;
+      const float bv = L0 - se.s;
+      const float dd = av - bv;
+      const float td = sfu::ex2(-fabsf(dd) * sfu::kLog2e);
+      const float ud = 1.0f + td;
+      const float inv = sfu::rcp(ud);
+      r = (dd >= 0.f) ? inv : td * inv;
+      ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv));
+      geta = se.inr ? (r - se.p) : 0.f;
+    } else {
+      const LogSig<T> se = log_sigmoid_pair<T>(eta);
+      const T av = se.lp + L1;
+      const T bv = se.l1mp + L0;
+      const T dd = av - bv;
+      const T td = N::exp_(-N::abs_(dd));
+      const T inv = N::rcp_(T(1) + td);
+      r = (dd >= T(0)) ? inv : td * inv;
+      ell = N::max_(av, bv) + N::log1p_(td);
+      geta = se.inr ? (r - se.p) : T(0);
+    }
     q[0] = ell;
     q[1] = geta;
 #pragma unroll
@@ -183,9 +206,9 @@ struct OccuModel {
   }
 };
 
-template <typename T, int KS, int KO, bool FP, int MINB>
+template <typename T, int KS, int KO, bool FP, bool STRICT, int MINB>
 static cudaError_t launch_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t stream, int* occ) {
-  auto kern = eval_kernel<T, OccuModel<T, KS, KO, FP>, MINB>;
+  auto kern = eval_kernel<T, OccuModel<T, KS, KO, FP, STRICT>, MINB>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -203,20 +226,22 @@ int occu_has_specialisation(int ks, int ko, bool fp) {
   return (ks == 1 && ko == 1) || (ks == 2 && ko == 1) || (ks == 5 && ko == 3);
 }
 
-template <typename T>
+template <typename T, bool STRICT>
 static cudaError_t dispatch(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
   const int ks = p.L.ks, ko = p.L.ko;
   const bool fp = (p.flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) != 0;
   constexpr int MB = sizeof(T) == 4 ? 3 : 2;
-  if (fp) return launch_one<T, -1, -1, true, 2>(p, grid, smem, st, occ);
-  if (ks == 1 && ko == 1) return launch_one<T, 1, 1, false, MB>(p, grid, smem, st, occ);
-  if (ks == 2 && ko == 1) return launch_one<T, 2, 1, false, MB>(p, grid, smem, st, occ);
-  if (ks == 5 && ko == 3) return launch_one<T, 5, 3, false, MB>(p, grid, smem, st, occ);
-  return launch_one<T, -1, -1, false, 2>(p, grid, smem, st, occ);
+  if (fp) return launch_one<T, -1, -1, true, true, 2>(p, grid, smem, st, occ);
+  if (ks == 1 && ko == 1) return launch_one<T, 1, 1, false, STRICT, MB>(p, grid, smem, st, occ);
+  if (ks == 2 && ko == 1) return launch_one<T, 2, 1, false, STRICT, MB>(p, grid, smem, st, occ);
+  if (ks == 5 && ko == 3) return launch_one<T, 5, 3, false, STRICT, MB>(p, grid, smem, st, occ);
+  return launch_one<T, -1, -1, false, STRICT, 2>(p, grid, smem, st, occ);
 }
 
 cudaError_t launch_occu(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ) {
-  return dtype == BL_F32 ? dispatch<float>(p, grid, smem, stream, occ) : dispatch<double>(p, grid, smem, stream, occ);
+  if (dtype == BL_F64) return dispatch<double, true>(p, grid, smem, stream, occ);
+  return (p.flags & BL_FLAG_STRICT_MATH) ? dispatch<float, true>(p, grid, smem, stream, occ)
+                                         : dispatch<float, false>(p, grid, smem, stream, occ);
 }
 
 int occu_derived_slots(uint32_t flags) {

@@ -3,19 +3,116 @@
 //   lane  = chain: every thread keeps ONE chain's beta/alpha in registers and its 1+D running sums
 //           (fp32 inside a tile, fp64 across tiles) -> no cross-lane reduction anywhere in the loop;
 //   site  = warp-broadcast: all lanes read the same packed fields (conflict-free broadcast LDS.128
-//           covering NS = 4 consecutive sites of the "SoA in tile" layout at once -> 4-way ILP);
+//           covering NS consecutive sites of the "SoA in tile" layout at once -> NS-way ILP);
 //   block = 256 chains x a contiguous range of site tiles, staged by TMA (cp.async.bulk) through the
 //           same mbarrier ring as the site-parallel engine; grid = (site splits, chain chunks).
+//   Per tile the y / mask bit words are expanded once, cooperatively, into 0/1 floats in shared
+//   memory (2 values per thread), and a block-uniform flag selects a mask-free inner loop when the
+//   tile has no missing visit.
 // The arithmetic is the closed form of oracle/occupancy.py:occu_logp_grad (reference:
 // biolith/models/occu.py:182-242, regression/linear.py:59-66) with bounded-error SFU math
 // (common.cuh sfu::softsig).  fp32, no false-positive extras; everything else uses the engine path.
+#include <cstdlib>
+
 #include "engine.cuh"
 
 namespace bl {
 
-constexpr int kNS = 4;  // sites processed together by one thread (one LDS.128 per field)
+template <int NS> struct VecLoad;
+template <> struct VecLoad<4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct VecLoad<2> {
+  static __device__ __forceinline__ void ld(const float* p, float (&o)[2]) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    o[0] = v.x; o[1] = v.y;
+  }
+};
 
-template <int KS, int KO, int MINB>
+// One warp-tile (<= 32 sites) for this thread's chain: adds into acc[1 + KB + KA].
+template <int KS, int KO, int NS, bool MASKED>
+__device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const float* __restrict__ yfx,
+                                           const float* __restrict__ mfx, const Layout& L, int n_valid,
+                                           const float (&b)[KS + 1], const float (&a)[KO + 1],
+                                           float (&acc)[3 + KS + KO]) {
+  constexpr int KB = KS + 1;
+  const int J = L.J;
+  const float log_tiny = Num<float>::log_tiny();
+  for (int g0 = 0; g0 < n_valid; g0 += NS) {
+    float x[KS > 0 ? KS : 1][NS], eta[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) eta[i] = b[0];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      VecLoad<NS>::ld(tile + k * kWarp + g0, x[k]);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) eta[i] = fmaf(x[k][i], b[1 + k], eta[i]);
+    }
+    float L1[NS], ga0[NS], ga[KO > 0 ? KO : 1][NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      L1[i] = 0.f; ga0[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < KO; ++k) ga[k][i] = 0.f;
+    }
+#pragma unroll 2
+    for (int j = 0; j < J; ++j) {
+      float w[KO > 0 ? KO : 1][NS], nu[NS], yf[NS], mf[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) nu[i] = a[0];
+#pragma unroll
+      for (int k = 0; k < KO; ++k) {
+        VecLoad<NS>::ld(tile + (L.off_w + j * KO + k) * kWarp + g0, w[k]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) nu[i] = fmaf(w[k][i], a[1 + k], nu[i]);
+      }
+      VecLoad<NS>::ld(yfx + j * kWarp + g0, yf);
+      if (MASKED) VecLoad<NS>::ld(mfx + j * kWarp + g0, mf);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const sfu::SoftSig ss = sfu::softsig<true>(nu[i]);
+        // log-lik term  y*xc - softplus(xc);  d/dnu = y - p  (zero outside the clamp range)
+        float term = fmaf(yf[i], ss.xc, -ss.s);
+        float g = ss.inr ? (yf[i] - ss.p) : 0.f;
+        if (MASKED) { term *= mf[i]; g *= mf[i]; }
+        L1[i] += term;
+        ga0[i] += g;
+#pragma unroll
+        for (int k = 0; k < KO; ++k) ga[k][i] = fmaf(g, w[k][i], ga[k][i]);
+      }
+    }
+    float n1[NS];
+    VecLoad<NS>::ld(tile + L.off_n1 * kWarp + g0, n1);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const float vf = (g0 + i < n_valid) ? 1.f : 0.f;
+      const sfu::SoftSig se = sfu::softsig<true>(eta[i]);
+      const float av = (se.xc - se.s) + L1[i];   // log psi~ + L1
+      const float bv = n1[i] * log_tiny - se.s;  // log1p(-psi~) + L0   (L0 = n1 log tiny)
+      // logaddexp(av, bv) and r = sigmoid(av - bv); no clamp on d
+      const float d = av - bv;
+      const float td = sfu::ex2(-fabsf(d) * sfu::kLog2e);
+      const float ud = 1.0f + td;
+      const float invd = sfu::rcp(ud);
+      const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
+      const float r = rr * vf;
+      const float ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv)) * vf;
+      const float geta = se.inr ? (rr - se.p) * vf : 0.f;
+      acc[0] += ell;
+      acc[1] += geta;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) acc[2 + k] = fmaf(geta, x[k][i], acc[2 + k]);
+      acc[1 + KB] = fmaf(r, ga0[i], acc[1 + KB]);
+#pragma unroll
+      for (int k = 0; k < KO; ++k) acc[2 + KB + k] = fmaf(r, ga[k][i], acc[2 + KB + k]);
+    }
+  }
+}
+
+template <int KS, int KO, int NS, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) occu_chain_kernel(const EvalParams p) {
   constexpr int KB = KS + 1, KA = KO + 1, NQ = 1 + KB + KA;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -23,9 +120,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) occu_chain_kernel(const E
   float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
   __shared__ int s_is_last;
   const int F = p.L.F, J = p.L.J;
-  const int WS = p.WS;  // warp-tiles per stage
-  const uint32_t tile_elems = (uint32_t)WS * F * kWarp;
+  const uint32_t tile_elems = (uint32_t)F * kWarp;  // one warp-tile per stage
   const uint32_t tile_bytes = tile_elems * sizeof(float);
+  float* yfx = stage0 + (size_t)p.nstage * tile_elems;  // [J][32] expanded detections
+  float* mfx = yfx + (size_t)J * kWarp;                 // [J][32] expanded mask
   const int tid = threadIdx.x;
   const int c0 = blockIdx.y * p.CB;
   const int ncb = min(p.CB, p.C - c0);
@@ -61,102 +159,31 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) occu_chain_kernel(const E
     }
   }
 
-  const float log_tiny = Num<float>::log_tiny();
   for (int it = 0; it < n_it; ++it) {
     const int s = it % p.nstage;
     mbar_wait(&bars[s], (uint32_t)((it / p.nstage) & 1));
-    for (int wt = 0; wt < WS; ++wt) {
-      const float* tile = stage0 + (size_t)s * tile_elems + (size_t)wt * F * kWarp;
-      const int64_t unit0 = ((bt_begin + it) * WS + wt) * kWarp;
-      const int n_valid = (int)max((int64_t)0, min((int64_t)kWarp, p.L.n_units - unit0));
-      float acc[NQ];
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
-      for (int g0 = 0; g0 < n_valid; g0 += kNS) {
-        // ---- site-level linear predictor for NS sites
-        float x[KS > 0 ? KS : 1][kNS], eta[kNS];
-#pragma unroll
-        for (int i = 0; i < kNS; ++i) eta[i] = b[0];
-#pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + k * kWarp + g0);
-          x[k][0] = v.x; x[k][1] = v.y; x[k][2] = v.z; x[k][3] = v.w;
-#pragma unroll
-          for (int i = 0; i < kNS; ++i) eta[i] = fmaf(x[k][i], b[1 + k], eta[i]);
-        }
-        float L1[kNS], ga0[kNS], ga[KO > 0 ? KO : 1][kNS];
-#pragma unroll
-        for (int i = 0; i < kNS; ++i) {
-          L1[i] = 0.f; ga0[i] = 0.f;
-#pragma unroll
-          for (int k = 0; k < KO; ++k) ga[k][i] = 0.f;
-        }
-        uint32_t yw[kNS], mw[kNS];
-        // ---- visits
-#pragma unroll 2
-        for (int j = 0; j < J; ++j) {
-          if ((j & 31) == 0) {
-            const uint4 yv = *reinterpret_cast<const uint4*>(tile + (p.L.off_y + (j >> 5)) * kWarp + g0);
-            const uint4 mv = *reinterpret_cast<const uint4*>(tile + (p.L.off_m + (j >> 5)) * kWarp + g0);
-            yw[0] = yv.x; yw[1] = yv.y; yw[2] = yv.z; yw[3] = yv.w;
-            mw[0] = mv.x; mw[1] = mv.y; mw[2] = mv.z; mw[3] = mv.w;
-          }
-          float w[KO > 0 ? KO : 1][kNS], nu[kNS];
-#pragma unroll
-          for (int i = 0; i < kNS; ++i) nu[i] = a[0];
-#pragma unroll
-          for (int k = 0; k < KO; ++k) {
-            const float4 v = *reinterpret_cast<const float4*>(tile + (p.L.off_w + j * KO + k) * kWarp + g0);
-            w[k][0] = v.x; w[k][1] = v.y; w[k][2] = v.z; w[k][3] = v.w;
-#pragma unroll
-            for (int i = 0; i < kNS; ++i) nu[i] = fmaf(w[k][i], a[1 + k], nu[i]);
-          }
-          const uint32_t bit = 1u << (j & 31);
-#pragma unroll
-          for (int i = 0; i < kNS; ++i) {
-            const sfu::SoftSig ss = sfu::softsig<true>(nu[i]);
-            const bool y = (yw[i] & bit) != 0, m = (mw[i] & bit) != 0;
-            // log-lik term  y*xc - softplus(xc);  d/dnu = y - p  (zero outside the clamp range)
-            float term = (y ? ss.xc : 0.f) - ss.s;
-            float g = (y ? 1.f : 0.f) - ss.p;
-            g = (ss.inr && m) ? g : 0.f;
-            term = m ? term : 0.f;
-            L1[i] += term;
-            ga0[i] += g;
-#pragma unroll
-            for (int k = 0; k < KO; ++k) ga[k][i] = fmaf(g, w[k][i], ga[k][i]);
-          }
-        }
-        // ---- marginalise z, accumulate this chain's sums
-        const float4 n1v = *reinterpret_cast<const float4*>(tile + p.L.off_n1 * kWarp + g0);
-        const float n1[kNS] = {n1v.x, n1v.y, n1v.z, n1v.w};
-#pragma unroll
-        for (int i = 0; i < kNS; ++i) {
-          const float vf = (g0 + i < n_valid) ? 1.f : 0.f;
-          const sfu::SoftSig se = sfu::softsig<true>(eta[i]);
-          const float av = (se.xc - se.s) + L1[i];       // log psi~ + L1
-          const float bv = n1[i] * log_tiny - se.s;      // log1p(-psi~) + L0
-          // logaddexp(av, bv) and r = sigmoid(av - bv), no clamp on d
-          const float d = av - bv;
-          const float td = sfu::ex2(-fabsf(d) * sfu::kLog2e);
-          const float ud = 1.0f + td;
-          const float invd = sfu::rcp(ud);
-          const float rr = (d >= 0.f) ? invd : td * invd;            // P(z = 1 | y)
-          const float r = rr * vf;
-          const float ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv)) * vf;
-          const float geta = se.inr ? (rr - se.p) * vf : 0.f;
-          acc[0] += ell;
-          acc[1] += geta;
-#pragma unroll
-          for (int k = 0; k < KS; ++k) acc[2 + k] = fmaf(geta, x[k][i], acc[2 + k]);
-          acc[1 + KB] = fmaf(r, ga0[i], acc[1 + KB]);
-#pragma unroll
-          for (int k = 0; k < KO; ++k) acc[2 + KB + k] = fmaf(r, ga[k][i], acc[2 + KB + k]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) acc64[i] += (double)acc[i];
+    const float* tile = stage0 + (size_t)s * tile_elems;
+    const int64_t unit0 = (bt_begin + it) * kWarp;
+    const int n_valid = (int)max((int64_t)0, min((int64_t)kWarp, p.L.n_units - unit0));
+    // expand y / mask bits of this tile to floats, once for the whole block
+    int any_masked = 0;
+    for (int e = tid; e < J * kWarp; e += kBlockThreads) {
+      const int site = e & 31, j = e >> 5;
+      const uint32_t yw = __float_as_uint(tile[(p.L.off_y + (j >> 5)) * kWarp + site]);
+      const uint32_t mw = __float_as_uint(tile[(p.L.off_m + (j >> 5)) * kWarp + site]);
+      const bool mb = (mw >> (j & 31)) & 1u;
+      yfx[e] = ((yw >> (j & 31)) & 1u) ? 1.f : 0.f;
+      mfx[e] = mb ? 1.f : 0.f;
+      any_masked |= (!mb && site < n_valid);
     }
+    any_masked = __syncthreads_or(any_masked);
+    float acc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
+    if (any_masked) chain_tile<KS, KO, NS, true>(tile, yfx, mfx, p.L, n_valid, b, a, acc);
+    else chain_tile<KS, KO, NS, false>(tile, yfx, mfx, p.L, n_valid, b, a, acc);
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc64[i] += (double)acc[i];
     __syncthreads();
     if (tid == 0 && it + p.nstage < n_it) {
       mbar_expect_tx(&bars[s], tile_bytes);
@@ -172,9 +199,9 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) occu_chain_kernel(const E
   finish_block<float>(p, c0, ncb, &s_is_last);
 }
 
-template <int KS, int KO, int MINB>
+template <int KS, int KO, int NS, int MINB>
 static cudaError_t launch_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = occu_chain_kernel<KS, KO, MINB>;
+  auto kern = occu_chain_kernel<KS, KO, NS, MINB>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -186,18 +213,39 @@ static cudaError_t launch_chain_one(const EvalParams& p, dim3 grid, size_t smem,
   return cudaGetLastError();
 }
 
-// chain-parallel path exists for fp32, no extras, these (Ks, Ko) and J a multiple of... any J
+// chain-parallel path exists for fp32, no extras, and these (Ks, Ko); any J
 bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32) return false;
   if (flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) return false;
   return (ks == 1 && ko == 1) || (ks == 2 && ko == 1) || (ks == 5 && ko == 3);
 }
 
+size_t occu_chain_smem(const Layout& L, int nstage) {
+  return 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
+}
+
+// (NS, min blocks/SM) variants of the headline shape; BL_CHAIN_VARIANT picks one for tuning runs
+static int chain_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BL_CHAIN_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
   const int ks = p.L.ks, ko = p.L.ko;
-  if (ks == 1 && ko == 1) return launch_chain_one<1, 1, 2>(p, grid, smem, st, occ);
-  if (ks == 2 && ko == 1) return launch_chain_one<2, 1, 2>(p, grid, smem, st, occ);
-  if (ks == 5 && ko == 3) return launch_chain_one<5, 3, 2>(p, grid, smem, st, occ);
+  if (ks == 1 && ko == 1) return launch_chain_one<1, 1, 4, 2>(p, grid, smem, st, occ);
+  if (ks == 2 && ko == 1) return launch_chain_one<2, 1, 4, 2>(p, grid, smem, st, occ);
+  if (ks == 5 && ko == 3) {
+    switch (chain_variant()) {
+      case 1: return launch_chain_one<5, 3, 2, 3>(p, grid, smem, st, occ);
+      case 2: return launch_chain_one<5, 3, 2, 2>(p, grid, smem, st, occ);
+      case 3: return launch_chain_one<5, 3, 4, 3>(p, grid, smem, st, occ);
+      default: return launch_chain_one<5, 3, 4, 2>(p, grid, smem, st, occ);
+    }
+  }
   return cudaErrorNotSupported;
 }
 

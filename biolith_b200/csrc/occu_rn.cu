@@ -1,6 +1,281 @@
+// K2: fused log-marginal + gradient of the Royle-Nichols abundance-induced heterogeneity model.
+//
+// Replaces value_and_grad(potential_fn) of biolith/models/occu_rn.py:175-222 (reference): per unit
+//   eta = beta0 + X.beta_1:, lambda = exp(eta)                              (occu_rn.py:181-188)
+//   N ~ Categorical(logits_k = k eta - lambda - lgamma(k+1)), k = 0..K      (utils/distributions.py:31-40,
+//                                                                            normalised by CategoricalLogits)
+//   r_j = sigmoid(alpha0 + W_j.alpha_1:),  P_kj = 1 - (1-c)(1-r_j)^k         (occu_rn.py:205-222)
+//   A_k = log pi_k + sum_j m_j Bernoulli(P~_kj).log_prob(y_j);  l = logsumexp_k A_k
+//   dl/deta = E_post[k] - E_prior[k];  dl/dnu_j = sum_k w_k dt_kj/dnu
+// log(1 - P_kj) = k log(1-r_j) + log(1-c) is carried in log space and 1 - q^k by the all-positive
+// recurrence P_k = P_{k-1} + q^{k-1} r, so neither the clamp decisions nor small P suffer the
+// 1-(1-r)**N cancellation of the reference formulation (oracle/occupancy.py:occu_rn_logp_grad).
+// Per-thread state A_k lives in shared memory ([K+1][256], conflict-free), visits outer / k inner.
+#include <cmath>
+#include <mutex>
+#include <type_traits>
+
 #include "engine.cuh"
+
 namespace bl {
-cudaError_t launch_occu_rn(const EvalParams&, int, dim3, size_t, cudaStream_t, int*) { return cudaErrorNotSupported; }
-int occu_rn_derived_slots(uint32_t) { return 0; }
-size_t occu_rn_extra_smem(const Layout&, int, int) { return 0; }
+
+constexpr int kMaxAbundance = 1023;
+__constant__ double c_lgamma[kMaxAbundance + 1];  // lgamma(k + 1)
+
+template <typename T, int KS, int KO, bool STRICT>
+struct OccuRnModel {
+  using N = Num<T>;
+  static constexpr bool kSfu = std::is_same<T, float>::value && !STRICT;
+  using M = Mth<T, kSfu>;
+  static constexpr bool kGeneric = (KS < 0);
+  static constexpr int KSM = kGeneric ? kMaxCov : KS;
+  static constexpr int KOM = kGeneric ? kMaxCov : KO;
+  static constexpr int kNQMax = kGeneric ? (1 + 2 * (kMaxCov + 1) + 1) : 33;  // runtime NQ loop either way
+  static constexpr int kDerived = 4;  // l1mc = log(1-c), c, 1-c, dc/dx = c(1-c)
+
+  struct Site {
+    T x[KSM];
+  };
+
+  static __device__ __forceinline__ void derive(const EvalParams& p, T* th) {
+    T* d = th + p.D;
+    if (p.flags & BL_FLAG_FP_CONSTANT) {
+      const T x = th[p.D - 1];
+      const T cv = T(1) / (T(1) + N::exp_(-x));
+      d[0] = -(N::max_(x, T(0)) + N::log1p_(N::exp_(-N::abs_(x))));
+      d[1] = cv;
+      d[2] = T(1) - cv;
+      d[3] = cv * (T(1) - cv);
+    } else {
+      d[0] = T(0); d[1] = T(0); d[2] = T(1); d[3] = T(0);
+    }
+  }
+
+  static __device__ __forceinline__ void load_site(const EvalParams& p, const T* __restrict__ tile, int lane,
+                                                   Site& s) {
+    const int ks = kGeneric ? p.L.ks : KS;
+#pragma unroll
+    for (int k = 0; k < KSM; ++k) s.x[k] = (k < ks) ? tile[k * kWarp + lane] : T(0);
+  }
+
+  static __device__ __forceinline__ void site_chain(const EvalParams& p, const T* __restrict__ tile, int lane,
+                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // per-thread column A[k] at scratch[k * 256 + tid] (placed after the engine's regions)
+    // (or, when (K+1) x 256 elements do not fit, at global scratch[k * n_threads + gtid], coalesced)
+    T* A;
+    size_t ST;
+    if (p.rn_scratch_global) {
+      ST = (size_t)gridDim.x * gridDim.y * kBlockThreads;
+      A = reinterpret_cast<T*>(p.rn_scratch_global) +
+          ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kBlockThreads + threadIdx.x;
+    } else {
+      ST = kBlockThreads;
+      A = reinterpret_cast<T*>(smem_raw + p.rn_scratch_off) + threadIdx.x;
+    }
+    const int ks = kGeneric ? p.L.ks : KS;
+    const int ko = kGeneric ? p.L.ko : KO;
+    const int J = p.L.J, K = p.K;
+    const bool fpc = (p.flags & BL_FLAG_FP_CONSTANT) != 0;
+    const T l1mc = th[p.D + 0], cval = th[p.D + 1], omc = th[p.D + 2];
+    T eta = th[0];
+#pragma unroll
+    for (int k = 0; k < KSM; ++k)
+      if (k < ks) eta = N::fma_(s.x[k], th[1 + k], eta);
+    const T* al = th + ks + 1;
+    const T a0 = al[0];
+    T a[KOM];
+#pragma unroll
+    for (int k = 0; k < KOM; ++k) a[k] = (k < ko) ? al[1 + k] : T(0);
+
+    // ---- prior logits (the -lambda term cancels in the normalisation) and their normaliser
+    T Mp = -N::inf();
+    for (int k = 0; k <= K; ++k) {
+      const T lk = N::fma_((T)k, eta, -(T)c_lgamma[k]);
+      A[k * ST] = lk;
+      Mp = N::max_(Mp, lk);
+    }
+    T Zp = T(0), Ep = T(0);
+    for (int k = 0; k <= K; ++k) {
+      const T e = M::exp_(A[k * ST] - Mp);
+      Zp += e;
+      Ep = N::fma_((T)k, e, Ep);
+    }
+    const T logZp = Mp + M::log_(Zp);
+    Ep = Ep * M::rcp_(Zp);
+
+    // ---- pass 1: A_k += sum_j m_j log Bernoulli(y_j | P~_kj)
+    uint32_t yw = 0, mw = 0;
+    const T* wrow = tile + p.L.off_w * kWarp + lane;
+    for (int j = 0; j < J; ++j) {
+      if ((j & 31) == 0) {
+        yw = N::as_bits(tile[(p.L.off_y + (j >> 5)) * kWarp + lane]);
+        mw = N::as_bits(tile[(p.L.off_m + (j >> 5)) * kWarp + lane]);
+      }
+      if (!((mw >> (j & 31)) & 1u)) continue;
+      const bool y = (yw >> (j & 31)) & 1u;
+      T nu = a0;
+#pragma unroll
+      for (int k = 0; k < KOM; ++k)
+        if (k < ko) nu = N::fma_(wrow[(j * ko + k) * kWarp], a[k], nu);
+      T sp, r;
+      M::softsig(nu, sp, r);
+      const T u = -sp;  // log(1 - r)
+      if (!y) {
+        for (int k = 0; k <= K; ++k) {
+          const T lq = N::fma_((T)k, u, l1mc);
+          A[k * ST] += N::max_(lq, N::log_eps());  // P <= tiny gives -tiny == lq in this precision
+        }
+      } else {
+        const T qv = T(1) - r;
+        T qk = T(1), P0 = T(0);  // q^k and 1 - q^k (all-positive recurrence)
+        for (int k = 0; k <= K; ++k) {
+          const T lq = N::fma_((T)k, u, l1mc);
+          const T P = N::fma_(omc, P0, cval);  // c + (1-c)(1-q^k)
+          const bool lo = P <= -N::neg_tiny();
+          const bool hi = lq <= N::log_eps();
+          const T t = lo ? N::log_tiny() : (hi ? N::log1m_eps() : M::log_(P));
+          A[k * ST] += t;
+          P0 = N::fma_(qk, r, P0);
+          qk *= qv;
+        }
+      }
+    }
+    // ---- posterior over N
+    T Mx = -N::inf();
+    for (int k = 0; k <= K; ++k) Mx = N::max_(Mx, A[k * ST]);
+    T Z = T(0);
+    for (int k = 0; k <= K; ++k) {
+      const T e = M::exp_(A[k * ST] - Mx);
+      A[k * ST] = e;
+      Z += e;
+    }
+    const T iZ = M::rcp_(Z);
+    T Eq = T(0);
+    for (int k = 0; k <= K; ++k) {
+      const T w = A[k * ST] * iZ;
+      A[k * ST] = w;
+      Eq = N::fma_((T)k, w, Eq);
+    }
+    const T ell = (Mx + M::log_(Z)) - logZp;
+    const T geta = Eq - Ep;
+
+    // ---- pass 2: dl/dnu_j = sum_k w_k dt_kj/dnu  (and dl/dc)
+    T ga0 = T(0), gc = T(0);
+    T ga[KOM];
+#pragma unroll
+    for (int k = 0; k < KOM; ++k) ga[k] = T(0);
+    for (int j = 0; j < J; ++j) {
+      if ((j & 31) == 0) {
+        yw = N::as_bits(tile[(p.L.off_y + (j >> 5)) * kWarp + lane]);
+        mw = N::as_bits(tile[(p.L.off_m + (j >> 5)) * kWarp + lane]);
+      }
+      if (!((mw >> (j & 31)) & 1u)) continue;
+      const bool y = (yw >> (j & 31)) & 1u;
+      T w[KOM];
+      T nu = a0;
+#pragma unroll
+      for (int k = 0; k < KOM; ++k) {
+        w[k] = (k < ko) ? wrow[(j * ko + k) * kWarp] : T(0);
+        nu = N::fma_(w[k], a[k], nu);
+      }
+      T sp, r;
+      M::softsig(nu, sp, r);
+      const T u = -sp;
+      T g = T(0);  // sum_k w_k dt/dlq * k   (then times dlq/dnu = -r per unit k)
+      T gcj = T(0);
+      if (!y) {
+        for (int k = 0; k <= K; ++k) {
+          const T lq = N::fma_((T)k, u, l1mc);
+          const T wk = (lq > N::log_eps()) ? A[k * ST] : T(0);  // dt/dlq = 1 inside the clamp
+          g = N::fma_((T)k, wk, g);
+          gcj += wk;
+        }
+      } else {
+        const T qv = T(1) - r;
+        T qk = T(1), P0 = T(0);
+        for (int k = 0; k <= K; ++k) {
+          const T lq = N::fma_((T)k, u, l1mc);
+          const T P = N::fma_(omc, P0, cval);
+          const bool inr = (P > -N::neg_tiny()) && (lq > N::log_eps());
+          // dt/dlq = -(1-P)/P with 1-P = (1-c) q^k
+          const T dt = inr ? -(omc * qk) * M::rcp_(P) : T(0);
+          const T wd = A[k * ST] * dt;
+          g = N::fma_((T)k, wd, g);
+          gcj += wd;
+          P0 = N::fma_(qk, r, P0);
+          qk *= qv;
+        }
+      }
+      const T gnu = -r * g;  // dlq/dnu = -k r
+      ga0 += gnu;
+#pragma unroll
+      for (int k = 0; k < KOM; ++k)
+        if (k < ko) ga[k] = N::fma_(gnu, w[k], ga[k]);
+      gc += gcj;
+    }
+    q[0] = ell;
+    q[1] = geta;
+#pragma unroll
+    for (int k = 0; k < KSM; ++k)
+      if (k < ks) q[2 + k] = geta * s.x[k];
+    q[2 + ks] = ga0;
+#pragma unroll
+    for (int k = 0; k < KOM; ++k)
+      if (k < ko) q[3 + ks + k] = ga[k];
+    if (fpc) q[3 + ks + ko] = -gc * th[p.D + 3] / omc;  // dlq/dc = -1/(1-c); times dc/dx
+  }
+};
+
+template <typename T, int KS, int KO, bool STRICT>
+static cudaError_t launch_rn_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t stream, int* occ) {
+  auto kern = eval_kernel<T, OccuRnModel<T, KS, KO, STRICT>, 1>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kBlockThreads, smem);
+  kern<<<grid, kBlockThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t ensure_lgamma_table() {
+  static std::once_flag once;
+  static cudaError_t status = cudaSuccess;
+  // per device: constant memory is per context; guard by device id
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && done[dev]) return cudaSuccess;
+  double h[kMaxAbundance + 1];
+  for (int k = 0; k <= kMaxAbundance; ++k) h[k] = std::lgamma((double)k + 1.0);
+  status = cudaMemcpyToSymbol(c_lgamma, h, sizeof(h));
+  if (status == cudaSuccess && dev < 64) done[dev] = true;
+  (void)once;
+  return status;
+}
+
+cudaError_t launch_occu_rn(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ) {
+  if (!occ) {
+    cudaError_t e = ensure_lgamma_table();
+    if (e != cudaSuccess) return e;
+  }
+  const bool strict = (p.flags & BL_FLAG_STRICT_MATH) != 0;
+  const bool s53 = p.L.ks == 5 && p.L.ko == 3;
+  if (dtype == BL_F64)
+    return s53 ? launch_rn_one<double, 5, 3, true>(p, grid, smem, stream, occ)
+               : launch_rn_one<double, -1, -1, true>(p, grid, smem, stream, occ);
+  if (strict)
+    return s53 ? launch_rn_one<float, 5, 3, true>(p, grid, smem, stream, occ)
+               : launch_rn_one<float, -1, -1, true>(p, grid, smem, stream, occ);
+  return s53 ? launch_rn_one<float, 5, 3, false>(p, grid, smem, stream, occ)
+             : launch_rn_one<float, -1, -1, false>(p, grid, smem, stream, occ);
+}
+
+int occu_rn_derived_slots(uint32_t) { return 4; }
+
+size_t occu_rn_extra_smem(const Layout&, int K, int elem) { return (size_t)(K + 1) * kBlockThreads * elem + 128; }
+
 }  // namespace bl

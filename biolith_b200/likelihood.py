@@ -59,6 +59,7 @@ class OccupancyLikelihood:
         max_abundance: int = 100,
         dtype: str = "float32",
         prior: bool = True,
+        strict_math: bool = False,
         prior_beta: Tuple[float, float] = (0.0, 1.0),
         prior_alpha: Tuple[float, float] = (0.0, 1.0),
         prior_fp_beta: Tuple[float, float] = (2.0, 5.0),
@@ -103,7 +104,8 @@ class OccupancyLikelihood:
         W = np.ascontiguousarray(obs_covs, dtype=data_dt)
         T = None if session_duration is None else np.ascontiguousarray(session_duration, dtype=data_dt)
         flags = (_lib.BL_FLAG_FP_CONSTANT if false_positives_constant else 0) | (
-            _lib.BL_FLAG_FP_UNOCCUPIED if false_positives_unoccupied else 0) | (_lib.BL_FLAG_PRIOR if prior else 0)
+            _lib.BL_FLAG_FP_UNOCCUPIED if false_positives_unoccupied else 0) | (_lib.BL_FLAG_PRIOR if prior else 0) | (
+            _lib.BL_FLAG_STRICT_MATH if strict_math else 0)
         d = bl_desc(
             abi_version=_lib.BL_ABI_VERSION, model=_lib.BL_MODEL[model], dtype=code,
             data_dtype=_lib.BL_F64 if data_dt == np.float64 else _lib.BL_F32, flags=flags, device=device,

@@ -11,7 +11,7 @@ from conftest import GOLDEN_NAMES, load_golden
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = {"occu"}
+IMPLEMENTED = {"occu", "occu_rn", "occu_cop"}
 RTOL = {"float32": 1e-5, "float64": 1e-10}
 
 
@@ -201,3 +201,18 @@ def test_config2_full_size_against_c_oracle():
         lp_b, gr_b = lk.logp_and_grad(th[300:])
         np.testing.assert_allclose(np.concatenate([lp_a, lp_b]), lp, rtol=1e-6)
         np.testing.assert_allclose(np.concatenate([gr_a, gr_b]), gr, rtol=1e-5, atol=1e-5 * np.abs(gr).max())
+
+
+@pytest.mark.parametrize("name", ["occu_5x3", "occu_missing", "rn_5x3", "cop_missing_5x3"])
+def test_strict_math_flag(name):
+    """BL_FLAG_STRICT_MATH (libm expf/log1pf/IEEE division) and the default bounded-error SFU forms
+    both meet the fp32 tolerance; their mutual difference is at fp32-rounding level."""
+    g = load_golden(name)
+    th = np.tile(g["thetas"], (12, 1))  # 84 chains -> the chain-parallel kernel where it exists
+    ref_lp = np.tile(g["logp_f32"], 12)
+    ref_gr = np.tile(g["grad_f32"], (12, 1))
+    with _make(g, "float32", strict_math=True) as strict, _make(g, "float32") as fast:
+        lp_s, gr_s = strict.logp_and_grad(th)
+        lp_f, gr_f = fast.logp_and_grad(th)
+    assert_close(lp_s, gr_s, ref_lp, ref_gr, 1e-5, f"{name}/strict")
+    assert_close(lp_f, gr_f, ref_lp, ref_gr, 1e-5, f"{name}/sfu")
