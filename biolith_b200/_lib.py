@@ -44,6 +44,15 @@ class bl_info(C.Structure):
     ]
 
 
+class bl_nuts_config(C.Structure):
+    _fields_ = [
+        ("n_chains", C.c_int32), ("num_warmup", C.c_int32), ("num_samples", C.c_int32),
+        ("max_tree_depth", C.c_int32), ("adapt_step_size", C.c_int32), ("adapt_mass_matrix", C.c_int32),
+        ("seed", C.c_uint64), ("target_accept_prob", C.c_double), ("init_step_size", C.c_double),
+        ("max_delta_energy", C.c_double),
+    ]
+
+
 _P = C.c_void_p
 # name -> (restype, argtypes); every symbol include/biolith_b200.h declares
 SIGNATURES = {
@@ -59,6 +68,10 @@ SIGNATURES = {
     "bl_eval": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "bl_eval_host": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "bl_eval_timed": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.POINTER(C.c_float)]),
+    "bl_nuts_create": (C.c_int, [_P, C.POINTER(bl_nuts_config), _P, C.POINTER(_P)]),
+    "bl_nuts_run": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "bl_nuts_get": (C.c_int, [_P] * 11),
+    "bl_nuts_destroy": (C.c_int, [_P]),
     "bl_device_malloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(_P)]),
     "bl_device_free": (C.c_int, [_P]),
     "bl_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),

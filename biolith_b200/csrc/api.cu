@@ -157,7 +157,8 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
   return BL_OK;
 }
 
-int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce) {
+int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce,
+                double* logp64) {
   Plan* pl = nullptr;
   int rc = plan_for(ds, C, &pl);
   if (rc) return rc;
@@ -165,6 +166,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   fill_params(ds, p);
   p.theta = theta;
   p.logp = logp;
+  p.logp64 = logp64;
   p.grad = grad;
   p.partial = ds->partial;
   p.counters = ds->counters;
@@ -402,7 +404,7 @@ int bl_eval(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp, voi
   if (!ds || !theta || !logp || !grad) return fail(BL_ERR_INVALID, "NULL argument");
   if (n_chains < 1) return fail(BL_ERR_INVALID, "n_chains must be >= 1");
   CU_TRY(cudaSetDevice(ds->desc.device));
-  return eval_device(ds, theta, n_chains, logp, grad, (cudaStream_t)stream, 0);
+  return eval_device(ds, theta, n_chains, logp, grad, (cudaStream_t)stream, 0, nullptr);
 }
 
 static int ensure_host_staging(bl_dataset* ds, int C) {
@@ -436,7 +438,7 @@ int bl_eval_host(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp
   CU_TRY(cudaMemcpyAsync(ds->d_theta, ds->h_theta, nt, cudaMemcpyHostToDevice, st));
   char* d_logp = (char*)ds->d_out;
   char* d_grad = d_logp + nl;
-  rc = eval_device(ds, ds->d_theta, n_chains, d_logp, d_grad, st, 0);
+  rc = eval_device(ds, ds->d_theta, n_chains, d_logp, d_grad, st, 0, nullptr);
   if (rc) return rc;
   CU_TRY(cudaMemcpyAsync(ds->h_out, ds->d_out, nl + nt, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));

@@ -263,6 +263,7 @@ struct EvalParams {
   const void* packed;      // packed dataset (element type = compute type)
   const void* theta;       // [C][D]
   void* logp;              // [C]
+  double* logp64;          // optional [C] fp64 copy of logp (NUTS energies), may be NULL
   void* grad;              // [C][D]
   double* partial;         // [nsplit][C][NQ] fp64 block partials
   unsigned int* counters;  // [n_chunks] "blocks done" tickets (self-resetting)

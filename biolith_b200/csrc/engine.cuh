@@ -51,6 +51,7 @@ __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, 
       }
     }
     logp[c] = (T)lp;
+    if (p.logp64) p.logp64[c] = lp;
   } else {
     const int i = q - 1;
     double g = total;

@@ -47,6 +47,7 @@ struct bl_dataset {
 
 namespace bl {
 int fail(int code, const char* fmt, ...);
-int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce);
+int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce,
+                double* logp64);
 extern std::atomic<int64_t> g_launches;
 }  // namespace bl

@@ -37,7 +37,7 @@ template <int KS, int KO, int NS, bool MASKED>
 __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const float* __restrict__ yfx,
                                            const float* __restrict__ mfx, const Layout& L, int n_valid,
                                            const float (&b)[KS + 1], const float (&a)[KO + 1],
-                                           float (&acc)[3 + KS + KO]) {
+                                           float (&acc)[3 + KS + KO], double& logp64) {
   constexpr int KB = KS + 1;
   const int J = L.J;
   const float log_tiny = Num<float>::log_tiny();
@@ -101,7 +101,7 @@ __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const
       const float r = rr * vf;
       const float ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv)) * vf;
       const float geta = se.inr ? (rr - se.p) * vf : 0.f;
-      acc[0] += ell;
+      logp64 += (double)ell;  // fp64 per unit: NUTS needs energy *differences* of a ~1e6-sized sum
       acc[1] += geta;
 #pragma unroll
       for (int k = 0; k < KS; ++k) acc[2 + k] = fmaf(geta, x[k][i], acc[2 + k]);
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) occu_chain_kernel(const E
     float acc[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
-    if (any_masked) chain_tile<KS, KO, NS, true>(tile, yfx, mfx, p.L, n_valid, b, a, acc);
-    else chain_tile<KS, KO, NS, false>(tile, yfx, mfx, p.L, n_valid, b, a, acc);
+    if (any_masked) chain_tile<KS, KO, NS, true>(tile, yfx, mfx, p.L, n_valid, b, a, acc, acc64[0]);
+    else chain_tile<KS, KO, NS, false>(tile, yfx, mfx, p.L, n_valid, b, a, acc, acc64[0]);
 #pragma unroll
     for (int i = 0; i < NQ; ++i) acc64[i] += (double)acc[i];
     __syncthreads();

@@ -1,0 +1,187 @@
+"""``fit`` with the signature of ``biolith.utils.fit`` (biolith/utils/fit.py:16-135), driving the
+B200 kernels + device-resident NUTS instead of numpyro's MCMC.
+
+Same positional/keyword surface (``model_fn, site_covs, obs_covs, obs, session_duration,
+num_samples, num_warmup, random_seed, num_chains, kernel, init_strategy, timeout, **kwargs``), same
+``FitResult(samples, mcmc)`` return, same sample names after ``rename_samples``
+(biolith/utils/data.py:145-165: ``cov_state_<name>``, ``cov_det_<name>``).  Anything outside the
+accelerated path (non-NUTS kernels, spatial / random effects, non-linear regressors, custom
+non-Normal priors) raises ``BiolithB200Error`` -- there is no fallback.
+"""
+
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import diagnostics as _diag
+from ._lib import BiolithB200Error
+from .likelihood import OccupancyLikelihood, _as_numpy
+from .models import REJECTED_IF_SET, SUPPORTED
+from .nuts import NutsSampler
+
+FitResult = namedtuple("FitResult", ["samples", "mcmc"])
+
+_MAX_DETERMINISTIC_ELEMS = 50_000_000
+
+
+def _covariate_names(arr, n):
+    if hasattr(arr, "columns"):
+        cols = list(arr.columns)
+        if getattr(arr.columns, "nlevels", 1) > 1:
+            cols = list(arr.columns.get_level_values(-1).unique())
+        return ["intercept"] + [str(c) for c in cols][:n]
+    return [str(0)] + [str(i + 1) for i in range(n)]
+
+
+class MCMCResult:
+    """Minimal stand-in for the ``numpyro.infer.MCMC`` object the reference returns."""
+
+    def __init__(self, model, grouped, extra, num_samples, num_chains, info):
+        self.model = model
+        self._grouped = grouped  # name -> (chains, draws, ...)
+        self._extra = extra
+        self.num_samples, self.num_chains = num_samples, num_chains
+        self.info = info
+
+    def get_samples(self, group_by_chain=False):
+        if group_by_chain:
+            return dict(self._grouped)
+        return {k: v.reshape((-1,) + v.shape[2:]) for k, v in self._grouped.items()}
+
+    def get_extra_fields(self, group_by_chain=False):
+        if group_by_chain:
+            return dict(self._extra)
+        return {k: v.reshape(-1) for k, v in self._extra.items()}
+
+    def summary(self, prob=0.9):
+        return _diag.summary(self._grouped, prob=prob)
+
+    def print_summary(self, prob=0.9):
+        s = self.summary(prob)
+        print(f"{'':>24s} {'mean':>10s} {'std':>10s} {'median':>10s} {'n_eff':>10s} {'r_hat':>8s}")
+        for name, d in s.items():
+            mean, std, med, ne, rh = (np.atleast_1d(d[k]).ravel() for k in ("mean", "std", "median", "n_eff", "r_hat"))
+            for i in range(mean.size):
+                print(f"{name + ('[%d]' % i if mean.size > 1 else ''):>24s} {mean[i]:10.4f} {std[i]:10.4f} "
+                      f"{med[i]:10.4f} {ne[i]:10.1f} {rh[i]:8.3f}")
+        div = int(self._extra["diverging"].sum())
+        print(f"Number of divergences: {div}")
+
+
+def fit(
+    model_fn: Callable,
+    site_covs=None,
+    obs_covs=None,
+    obs=None,
+    session_duration=None,
+    num_samples: int = 1000,
+    num_warmup: int = 1000,
+    random_seed: int = 0,
+    num_chains: int = 5,
+    kernel: Optional[str] = None,
+    init_strategy: Optional[Callable] = None,
+    timeout: Optional[int] = None,
+    *,
+    dtype: str = "float32",
+    device: int = 0,
+    max_tree_depth: int = 10,
+    target_accept_prob: float = 0.8,
+    **kwargs,
+) -> FitResult:
+    name = getattr(model_fn, "__name__", str(model_fn))
+    if name not in SUPPORTED:
+        raise BiolithB200Error(-2, "fit", f"model {name!r} is outside the accelerated path {sorted(SUPPORTED)}")
+    if kernel not in (None, "nuts"):
+        raise BiolithB200Error(-2, "fit", f"kernel={kernel!r}: only NUTS is implemented on the device")
+    if init_strategy is not None:
+        raise BiolithB200Error(-2, "fit", "custom init_strategy is not supported (init_to_uniform(radius=2) is used)")
+    for k, default in REJECTED_IF_SET.items():
+        if kwargs.get(k, default) not in (default, None, False):
+            raise BiolithB200Error(-2, "fit", f"{k} is outside the accelerated path (no fallback)")
+    for k in ("regressor_occ", "regressor_det", "regressor_abu"):
+        r = kwargs.get(k)
+        if r is not None and getattr(r, "__name__", "") != "LinearRegression":
+            raise BiolithB200Error(-2, "fit", f"{k}={r!r}: only LinearRegression is accelerated")
+    prior_kw = {}
+    for k, tgt in (("prior_beta", "prior_beta"), ("prior_alpha", "prior_alpha")):
+        pr = kwargs.get(k)
+        if pr is not None:
+            loc, scale = getattr(pr, "loc", None), getattr(pr, "scale", None)
+            if loc is None or scale is None or type(pr).__name__ != "Normal":
+                raise BiolithB200Error(-2, "fit", f"{k}: only Normal(loc, scale) priors are accelerated")
+            prior_kw[tgt] = (float(loc), float(scale))
+    n_species = kwargs.get("n_species", 1)
+    site_names = _covariate_names(site_covs, _as_numpy(site_covs).shape[1])
+    obs_np = _as_numpy(obs_covs)
+    obs_names = _covariate_names(obs_covs, obs_np.shape[-1] if obs_np.ndim >= 3 else 1)
+    if kwargs.pop("ell", None) is not None:
+        pass  # simulate() returns ell even without coords; meaningless without a spatial effect
+    fpc = bool(kwargs.get("false_positives_constant", False))
+    fpu = bool(kwargs.get("false_positives_unoccupied", False))
+    lk = OccupancyLikelihood(
+        name, site_covs, obs_covs, obs, session_duration, false_positives_constant=fpc,
+        false_positives_unoccupied=fpu, max_abundance=kwargs.get("max_abundance", 100), dtype=dtype, prior=True,
+        device=device, max_chains=num_chains, **prior_kw)
+    if n_species != 1 and _as_numpy(obs) is None:
+        raise BiolithB200Error(-2, "fit", "n_species > 1 needs one handle per species")
+    sampler = NutsSampler(lk, num_chains, num_warmup, num_samples, seed=random_seed,
+                          max_tree_depth=max_tree_depth, target_accept_prob=target_accept_prob)
+    complete = sampler.run(timeout=timeout)
+    if not complete:
+        sampler.close()
+        lk.close()
+        raise TimeoutError("sampling did not finish within the timeout")  # reference: utils/misc.py:11-21
+    res = sampler.results()
+    sampler.close()
+
+    th = res["samples"].astype(np.float64)  # (C, N, D)
+    Ks, Ko = lk.shape["n_site_covs"], lk.shape["n_obs_covs"]
+    grouped = {
+        "beta": th[:, :, None, : Ks + 1],  # (C, N, n_species, Kb) like numpyro's plate layout
+        "alpha": th[:, :, None, Ks + 1 : Ks + Ko + 2],
+    }
+    i = Ks + Ko + 2
+    if name == "occu_cop":
+        if fpc:
+            grouped["rate_fp_constant"] = np.exp(th[:, :, i]); i += 1
+        if fpu:
+            grouped["rate_fp_unoccupied"] = np.exp(th[:, :, i]); i += 1
+    else:
+        if fpc:
+            grouped["prob_fp_constant"] = 1 / (1 + np.exp(-th[:, :, i])); i += 1
+        if fpu:
+            grouped["prob_fp_unoccupied"] = 1 / (1 + np.exp(-th[:, :, i])); i += 1
+    # small problems: also materialise the deterministic site the reference's tests read
+    X = np.nan_to_num(np.asarray(_as_numpy(site_covs), dtype=np.float64))
+    S = X.shape[0]
+    if S * num_chains * num_samples <= _MAX_DETERMINISTIC_ELEMS:
+        eta = th[:, :, 0:1] + np.einsum("cnk,sk->cns", th[:, :, 1 : Ks + 1], X)
+        det = np.exp(eta) if name == "occu_rn" else 1 / (1 + np.exp(-eta))
+        grouped["abundance" if name == "occu_rn" else "psi"] = det[:, :, None, :, None]  # (C,N,P=1,S,Sp)
+    extra = dict(diverging=res["diverging"], accept_prob=res["accept_prob"], num_steps=res["num_steps"],
+                 potential_energy=res["potential_energy"])
+    info = dict(step_size=res["step_size"], inverse_mass_matrix=res["inverse_mass_matrix"],
+                leapfrogs=res["leapfrogs"], warmup_leapfrogs=res["warmup_leapfrogs"],
+                global_steps=res["global_steps"], wall_s=res["wall_s"], kernel_variant=lk.kernel_variant)
+    mcmc = MCMCResult(name, grouped, extra, num_samples, num_chains, info)
+    lk.close()
+    samples = mcmc.get_samples()
+    samples = rename_samples(samples, site_names, obs_names)
+    return FitResult(samples, mcmc)
+
+
+def rename_samples(samples, site_covs_names=None, obs_covs_names=None):
+    """Same renaming as biolith/utils/data.py:145-165."""
+    samples = dict(samples)
+    if site_covs_names is not None and "beta" in samples:
+        beta = samples.pop("beta")
+        for i, n in enumerate(site_covs_names):
+            samples[f"cov_state_{n}"] = beta[..., i]
+    if obs_covs_names is not None and "alpha" in samples:
+        alpha = samples.pop("alpha")
+        for i, n in enumerate(obs_covs_names):
+            samples[f"cov_det_{n}"] = alpha[..., i]
+    return samples
