@@ -162,6 +162,10 @@ def main():
     ap.add_argument("--cpu-chains", type=int, default=8, help="chain-evals per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"], help="site-sharded cross-rank sum")
+    ap.add_argument("--nuts-warmup", type=int, default=200)
+    ap.add_argument("--nuts-samples", type=int, default=100)
+    ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -191,7 +195,7 @@ def main():
     if shard == "sites" and world > 1:
         from biolith_b200 import sharded
 
-        comm = sharded.attach_site_sharding(lk, dist, rank, world, local_rank, chains)
+        comm = sharded.attach_site_sharding(lk, dist, rank, world, chains, mode=args.exchange)
     D = lk.theta_dim
     npdt = lk.np_dtype
     es = np.dtype(npdt).itemsize
@@ -252,6 +256,10 @@ def main():
     value = chains_total * args.steps / (total_ms * 1e-3)
     e2e_value = chains_total * args.steps / e2e_s
 
+    nuts = None
+    if not args.no_nuts:
+        nuts = run_nuts(args, lk, chains, rank, world, shard, dist)
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         alg_bytes = lk.algorithmic_bytes * chains  # C x B_eval per launch (per GPU)
@@ -281,12 +289,63 @@ def main():
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
+        if nuts is not None:
+            line["nuts"] = nuts
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains)
         print(json.dumps(line), flush=True)
     lk.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_nuts(args, lk, chains, rank, world, shard, dist):
+    """NUTS ESS/sec: device-resident chain-batched NUTS (numpyro defaults: target 0.8, depth 10, diag mass),
+    init U(-2,2); ESS by the numpyro.diagnostics definition over all chains of all ranks."""
+    import biolith_b200 as bb
+    from biolith_b200 import diagnostics as dg
+    from biolith_b200 import sharded
+
+    seed = 11 + (rank if shard == "chains" else 0)
+    s = bb.NutsSampler(lk, chains, args.nuts_warmup, args.nuts_samples, seed=seed)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ok = s.run(timeout=600)
+    wall = time.perf_counter() - t0
+    r = s.results()
+    s.close()
+    local = dict(samples=r["samples"], leapfrogs=r["leapfrogs"], warmup_leapfrogs=r["warmup_leapfrogs"],
+                 num_steps=r["num_steps"], accept_prob=r["accept_prob"], diverging=r["diverging"],
+                 step_size=r["step_size"], wall=np.array([wall]), steps=np.array([r["global_steps"]]),
+                 ok=np.array([ok]))
+    if dist is not None and shard == "chains":
+        g = sharded.gather_chain_results(dist, rank, world, local)
+    else:
+        g = local
+    if rank != 0:
+        return None
+    x = g["samples"].astype(np.float64)
+    wall = float(np.max(g["wall"]))
+    ne = dg.effective_sample_size(x)
+    rhat = dg.split_gelman_rubin(x)
+    leaps, wleaps = g["leapfrogs"].astype(np.float64), g["warmup_leapfrogs"].astype(np.float64)
+    frac_sampling = float((leaps - wleaps).sum() / leaps.sum())
+    return {
+        "ess_per_sec_min": float(ne.min() / wall), "ess_per_sec_median": float(np.median(ne) / wall),
+        "ess_per_sec_min_sampling_phase": float(ne.min() / (wall * frac_sampling)),
+        "ess_min": float(ne.min()), "ess_median": float(np.median(ne)), "r_hat_max": float(rhat.max()),
+        "chains": int(x.shape[0]), "num_warmup": args.nuts_warmup, "num_samples": args.nuts_samples,
+        "wall_s": wall, "complete": bool(np.all(g["ok"])), "global_steps": int(np.max(g["steps"])),
+        "ms_per_global_step": 1e3 * wall / max(int(np.max(g["steps"])), 1),
+        "leapfrogs_per_chain_mean": float(leaps.mean()), "leapfrogs_per_draw": float(g["num_steps"].mean()),
+        "useful_eval_frac": float(leaps.sum() / (x.shape[0] * max(int(np.max(g["steps"])), 1))) if shard == "chains"
+        else float(leaps.mean() / max(int(np.max(g["steps"])), 1)),
+        "accept_prob_mean": float(g["accept_prob"].mean()), "divergence_frac": float(g["diverging"].mean()),
+        "step_size_median": float(np.median(g["step_size"])),
+        "note": "wall includes warm-up; ESS = numpyro.diagnostics.effective_sample_size over all chains; "
+                "min/median over the %d parameters" % x.shape[2],
+    }
 
 
 def shard_is_chains(workload):

@@ -72,6 +72,12 @@ SIGNATURES = {
     "bl_nuts_run": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bl_nuts_get": (C.c_int, [_P] * 11),
     "bl_nuts_destroy": (C.c_int, [_P]),
+    "bl_comm_unique_id": (C.c_int, [_P, C.c_size_t]),
+    "bl_dataset_attach_nccl": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_int32]),
+    "bl_dataset_p2p_export": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t]),
+    "bl_dataset_p2p_attach": (C.c_int, [_P, _P, C.c_size_t]),
+    "bl_dataset_comm_error": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "bl_dataset_detach_comm": (C.c_int, [_P]),
     "bl_device_malloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(_P)]),
     "bl_device_free": (C.c_int, [_P]),
     "bl_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),

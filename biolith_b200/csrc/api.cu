@@ -41,6 +41,9 @@ bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 size_t occu_chain_smem(const Layout& L, int nstage);
 
+int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
+void comm_destroy(bl_dataset* ds);
+
 constexpr int kChainKernelMinChains = 64;
 
 static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st,
@@ -171,7 +174,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.partial = ds->partial;
   p.counters = ds->counters;
   p.sums = ds->sums;
-  p.allreduce = allreduce;
+  p.allreduce = (allreduce || ds->comm) ? 1 : 0;
   p.C = C;
   p.CB = pl->g.CB;
   p.WC = pl->g.WC;
@@ -186,6 +189,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
                                    : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
   if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (ds->comm) return comm_post_eval(ds, p, st);  // cross-rank sum of the raw sums, then priors
   return BL_OK;
 }
 
@@ -355,6 +359,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
 int bl_dataset_destroy(bl_dataset* ds) {
   if (!ds) return BL_OK;
   cudaSetDevice(ds->desc.device);
+  comm_destroy(ds);
   cudaFree(ds->packed); cudaFree(ds->partial); cudaFree(ds->counters); cudaFree(ds->sums);
   cudaFree(ds->rn_scratch);
   cudaFree(ds->d_theta); cudaFree(ds->d_out);

@@ -1,0 +1,71 @@
+"""CPU (gloo, world_size 2) tests of the multi-GPU host plumbing: site ranges, the NCCL-id /
+IPC-handle exchange pattern and the chain gather.  No GPU, no compute calls."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_ranges_partition_the_sites():
+    from biolith_b200.sharded import shard_data, shard_range
+
+    for n in (0, 1, 7, 8, 1_000_003):
+        for w in (1, 2, 3, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    X = np.arange(10)[:, None].astype(float)
+    W = np.zeros((10, 1, 3, 2))
+    y = np.zeros((1, 10, 1, 3))
+    a = shard_data(X, W, y, None, 0, 3)
+    assert a[0].shape[0] == 4 and a[1].shape[0] == 4 and a[2].shape == (1, 4, 1, 3)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from biolith_b200 import sharded
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        uid = sharded.exchange_unique_id(dist, rank, lambda: bytes(range(128)))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes([rank]) * sharded.IPC_HANDLE_BYTES)
+        local = dict(samples=np.full((3, 5, 2), float(rank)), step_size=np.full(3, 0.1 * (rank + 1)), wall_s=1.0)
+        g = sharded.gather_chain_results(dist, rank, world, local)
+        q.put((rank, uid == bytes(range(128)), [h[0] for h in handles], None if g is None else g["samples"].shape,
+               None if g is None else g["samples"][:, 0, 0].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_exchange_and_gather():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1]
+    assert res[0][2] == [0, 1] and res[1][2] == [0, 1]
+    assert res[0][3] == (6, 5, 2) and res[0][4] == [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
+    assert res[1][3] is None
