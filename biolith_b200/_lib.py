@@ -44,6 +44,10 @@ class bl_info(C.Structure):
     ]
 
 
+class bl_xla_opaque(C.Structure):
+    _fields_ = [("dataset", C.c_uint64), ("n_chains", C.c_int32), ("reserved", C.c_int32)]
+
+
 class bl_nuts_config(C.Structure):
     _fields_ = [
         ("n_chains", C.c_int32), ("num_warmup", C.c_int32), ("num_samples", C.c_int32),
@@ -78,6 +82,7 @@ SIGNATURES = {
     "bl_dataset_p2p_attach": (C.c_int, [_P, _P, C.c_size_t]),
     "bl_dataset_comm_error": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "bl_dataset_detach_comm": (C.c_int, [_P]),
+    "bl_xla_eval": (None, [_P, C.POINTER(_P), C.c_char_p, C.c_size_t, _P]),
     "bl_device_malloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(_P)]),
     "bl_device_free": (C.c_int, [_P]),
     "bl_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t, _P]),
