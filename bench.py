@@ -40,7 +40,13 @@ WORKLOADS = {
                            256, "sites"),
     "occu_small": ("occu", dict(n_site_covs=5, n_obs_covs=3, n_sites=20_000, deployment_days_per_site=56), 256,
                    "chains"),
+    # BASELINE.json configs[2] / configs[3] (parity-test shapes; timed here for DESIGN.md, not the headline)
+    "occu_rn_200k_x10_k50": ("occu_rn", dict(n_site_covs=5, n_obs_covs=3, n_sites=200_000,
+                                             deployment_days_per_site=70), 256, "chains"),
+    "occu_cop_500k_x12": ("occu_cop", dict(n_site_covs=5, n_obs_covs=3, n_sites=500_000,
+                                           deployment_days_per_site=84, simulate_missing=True), 1024, "chains"),
 }
+MODEL_KW = {"occu_rn": dict(max_abundance=50), "occu_cop": dict(false_positives_constant=True)}
 METRIC = "logp+grad evals/sec (occu, 1M sites x 8 visits, chain-batched)"
 UNIT = "chain-evals/s"
 
@@ -115,6 +121,8 @@ def make_data(workload, seed):
     X = data["site_covs"].astype(np.float32)   # the reference ingests as fp32 (utils/data.py:135-140)
     W = data["obs_covs"].astype(np.float32)
     y = data["obs"].astype(np.float32)
+    T = data.get("session_duration")
+    make_data.session_duration = None if T is None else T.astype(np.float32)
     return model, X, W, y, chains, shard
 
 
@@ -166,6 +174,7 @@ def main():
     ap.add_argument("--nuts-warmup", type=int, default=200)
     ap.add_argument("--nuts-samples", type=int, default=100)
     ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s section")
+    ap.add_argument("--strict-math", action="store_true", help="BL_FLAG_STRICT_MATH (libm expf/log1pf)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -191,7 +200,8 @@ def main():
     if args.chains:
         chains = args.chains
     comm = None
-    lk = bb.OccupancyLikelihood(model, X, W, y, dtype=args.dtype, device=local_rank, max_chains=chains)
+    lk = bb.OccupancyLikelihood(model, X, W, y, make_data.session_duration, dtype=args.dtype, device=local_rank,
+                                max_chains=chains, strict_math=args.strict_math, **MODEL_KW.get(model, {}))
     if shard == "sites" and world > 1:
         from biolith_b200 import sharded
 
@@ -269,7 +279,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "model": model, "sites": int(units_sites),
+            "config": {"workload": args.workload, "model": model, "strict_math": bool(args.strict_math), "sites": int(units_sites),
                        "visits": int(W.shape[2]), "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]),
                        "chains_per_gpu": chains, "chains_total": chains_total, "sharding": shard,
                        "theta": "U(-2,2) per chain (init_to_uniform)",
@@ -291,7 +301,7 @@ def main():
         }
         if nuts is not None:
             line["nuts"] = nuts
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and model == "occu":
             line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains)
         print(json.dumps(line), flush=True)
     lk.close()
