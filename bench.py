@@ -299,6 +299,15 @@ def main():
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
+        if model == "occu" and lk.kernel_variant == 1 and chains >= 64 and args.dtype == "float32" and not args.strict_math:
+            # the unit that actually binds the chain kernel (profiles/): 3 MUFU (ex2, lg2, rcp) per logistic
+            # term, (J + 2) terms per (site, chain); B200 SFU = 16 lanes / SM / clock
+            mufu = 3.0 * (W.shape[2] + 2) * X.shape[0] * chains
+            sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_mufu = 148 * 16 * sm_clock
+            line["roofline_sfu"] = {"bound": "sfu", "achieved": mufu / (ms_launch * 1e-3) / 1e12,
+                                    "peak": peak_mufu / 1e12, "unit": "T MUFU/s", "frac": mufu / (ms_launch * 1e-3) / peak_mufu,
+                                    "note": "secondary roofline: the kernel is issue/SFU bound, not HBM bound"}
         if nuts is not None:
             line["nuts"] = nuts
         if not args.no_cpu_baseline and world == 1 and model == "occu":

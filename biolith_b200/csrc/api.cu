@@ -39,7 +39,8 @@ int occu_cop_derived_slots(uint32_t flags);
 size_t occu_rn_extra_smem(const Layout& L, int K, int elem);
 bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
-size_t occu_chain_smem(const Layout& L, int nstage);
+size_t occu_chain_smem(const Layout& L, int nstage, int block_threads);
+int occu_chain_block_threads(int ks, int ko);
 
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
@@ -100,10 +101,13 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     pl.chain_kernel = ds->desc.model == BL_MODEL_OCCU && C >= kChainKernelMinChains && !ds->force_engine &&
                       occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags);
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
+      const int bt = occu_chain_block_threads(ds->L.ks, ds->L.ko);  // chains per block
+      pl.g.n_chunks = (C + bt - 1) / bt;
+      pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
       pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
       pl.g.n_block_tiles = ds->L.n_tiles;
       pl.g.nstage = kMaxStages;
-      pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage);
+      pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage, bt);
     }
     if (pl.g.smem_bytes > ds->smem_limit)
       return fail(BL_ERR_UNSUPPORTED, "shape needs %zu B of shared memory per block (> %zu)", pl.g.smem_bytes,
