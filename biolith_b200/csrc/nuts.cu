@@ -439,6 +439,9 @@ struct bl_nuts {
   cudaStream_t stream = nullptr;
   int64_t steps = 0;
   bool started = false;
+  // CUDA graph of `graph_steps` x (eval + advance): the inner loop is launch-bound on small datasets
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_steps = 0;
 };
 
 // numpyro build_adaptation_schedule (hmc_util.py): Stan's 75 / 25*2^k / 50 windows
@@ -480,6 +483,7 @@ int bl_nuts_destroy(bl_nuts* s) {
   cudaFree(s->d_grad); cudaFree(s->d_logp_t); cudaFree(s->d_logp64); cudaFree(s->p.samples);
   cudaFree(s->p.stat_accept); cudaFree(s->p.stat_steps); cudaFree(s->p.stat_div); cudaFree(s->p.stat_pe);
   cudaFree(s->p.n_done);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return BL_OK;
@@ -564,13 +568,42 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
     g_launches.fetch_add(1);
     s->started = true;
   }
+  auto one_step = [&]() -> int {
+    int rc = eval_device(ds, p.theta, p.C, s->d_logp_t, s->d_grad, s->stream, 0, s->d_logp64);
+    if (rc) return rc;
+    if (f32) nuts_advance_kernel<float><<<blocks, threads, 0, s->stream>>>(p);
+    else nuts_advance_kernel<double><<<blocks, threads, 0, s->stream>>>(p);
+    g_launches.fetch_add(1);
+    return BL_OK;
+  };
+  // Capture poll_every x (eval + advance) once and replay it (not with a cross-rank exchange attached:
+  // the P2P epoch is a kernel argument).  The plan / workspace already exist (the start eval ran).
+  if (!ds->comm && !s->graph_exec && max_steps >= poll_every && s->graph_steps == 0) {
+    s->graph_steps = -1;  // do not retry if capture is refused
+    cudaGraph_t graph = nullptr;
+    const int64_t launches_before = g_launches.load();
+    if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rc = BL_OK;
+      for (int k = 0; k < poll_every && rc == BL_OK; ++k) rc = one_step();
+      cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+      if (rc == BL_OK && ce == cudaSuccess && graph &&
+          cudaGraphInstantiate(&s->graph_exec, graph, 0) == cudaSuccess)
+        s->graph_steps = poll_every;
+      if (graph) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();
+    g_launches.store(launches_before);  // captured launches were not executed
+  }
   while (n < max_steps) {
-    for (int k = 0; k < poll_every && n < max_steps; ++k, ++n) {
-      int rc = eval_device(ds, p.theta, p.C, s->d_logp_t, s->d_grad, s->stream, 0, s->d_logp64);
-      if (rc) return rc;
-      if (f32) nuts_advance_kernel<float><<<blocks, threads, 0, s->stream>>>(p);
-      else nuts_advance_kernel<double><<<blocks, threads, 0, s->stream>>>(p);
-      g_launches.fetch_add(1);
+    if (s->graph_exec && max_steps - n >= s->graph_steps) {
+      CU_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
+      g_launches.fetch_add(2 * (int64_t)s->graph_steps);
+      n += s->graph_steps;
+    } else {
+      for (int k = 0; k < poll_every && n < max_steps; ++k, ++n) {
+        int rc = one_step();
+        if (rc) return rc;
+      }
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(&done, p.n_done, sizeof(int), cudaMemcpyDeviceToHost, s->stream));

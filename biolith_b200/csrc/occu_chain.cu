@@ -33,13 +33,13 @@ template <> struct VecLoad<2> {
 };
 
 // One warp-tile (<= 32 sites) for this thread's chain: adds into acc[1 + KB + KA].
-template <int KS, int KO, int NS, bool MASKED>
+template <int KS, int KO, int NS, bool MASKED, int JT>
 __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const float* __restrict__ yfx,
                                            const float* __restrict__ mfx, const Layout& L, int n_valid,
                                            const float (&b)[KS + 1], const float (&a)[KO + 1],
                                            float (&acc)[3 + KS + KO], double& logp64) {
   constexpr int KB = KS + 1;
-  const int J = L.J;
+  const int J = JT > 0 ? JT : L.J;
   const float log_tiny = Num<float>::log_tiny();
   for (int g0 = 0; g0 < n_valid; g0 += NS) {
     float x[KS > 0 ? KS : 1][NS], eta[NS];
@@ -58,7 +58,7 @@ __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const
 #pragma unroll
       for (int k = 0; k < KO; ++k) ga[k][i] = 0.f;
     }
-#pragma unroll 2
+#pragma unroll(JT > 0 ? JT : (JT < 0 ? -JT : 2))
     for (int j = 0; j < J; ++j) {
       float w[KO > 0 ? KO : 1][NS], nu[NS], yf[NS], mf[NS];
 #pragma unroll
@@ -112,7 +112,7 @@ __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const
   }
 }
 
-template <int KS, int KO, int NS, int MINB, int BT>
+template <int KS, int KO, int NS, int MINB, int BT, int JT>
 __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p) {
   constexpr int KB = KS + 1, KA = KO + 1, NQ = 1 + KB + KA;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p
     float acc[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
-    if (any_masked) chain_tile<KS, KO, NS, true>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
-    else chain_tile<KS, KO, NS, false>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
+    if (any_masked) chain_tile<KS, KO, NS, true, JT>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
+    else chain_tile<KS, KO, NS, false, JT>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
 #pragma unroll
     for (int i = 1; i < NQ; ++i) g64[(size_t)i * BT] += (double)acc[i];
     __syncthreads();
@@ -203,9 +203,9 @@ __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p
   finish_block<float>(p, c0, ncb, &s_is_last);
 }
 
-template <int KS, int KO, int NS, int MINB, int BT>
+template <int KS, int KO, int NS, int MINB, int BT, int JT = 0>
 static cudaError_t launch_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = occu_chain_kernel<KS, KO, NS, MINB, BT>;
+  auto kern = occu_chain_kernel<KS, KO, NS, MINB, BT, JT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -251,9 +251,13 @@ cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaS
   if (ks == 1 && ko == 1) return launch_chain_one<1, 1, 4, 2, 256>(p, grid, smem, st, occ);
   if (ks == 2 && ko == 1) return launch_chain_one<2, 1, 4, 2, 256>(p, grid, smem, st, occ);
   if (ks == 5 && ko == 3) {
-    // measured on B200 (config 2, ms per 1024-chain eval): 0: 9.70 | 2: 9.79 | (256 thr, 3 blocks/SM,
-    // 80 regs): 10.8 | (128 thr, 5 blocks/SM, 96 regs): 11.4 -> fewer, fatter warps win (XU-bound)
-    if (chain_variant() == 2) return launch_chain_one<5, 3, 4, 4, 128>(p, grid, smem, st, occ);
+    // measured on B200 (config 2, ms per 1024-chain eval): J compile-time (8 visits fully unrolled) 9.16 |
+    // runtime J unroll 2: 9.70, unroll 4: 10.35, unroll 1: 10.19 | 128 thr x 4 blocks: 9.79 |
+    // 256 thr x 3 blocks (80 regs): 10.8 | 128 thr x 5 blocks (96 regs): 11.4 -> fewer, fatter warps win
+    const int v = chain_variant();
+    if (v == 2) return launch_chain_one<5, 3, 4, 4, 128>(p, grid, smem, st, occ);
+    if (v == 3) return launch_chain_one<5, 3, 4, 2, 256, 0>(p, grid, smem, st, occ);
+    if (p.L.J == 8) return launch_chain_one<5, 3, 4, 2, 256, 8>(p, grid, smem, st, occ);
     return launch_chain_one<5, 3, 4, 2, 256>(p, grid, smem, st, occ);
   }
   return cudaErrorNotSupported;
