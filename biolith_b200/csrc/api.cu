@@ -41,6 +41,10 @@ bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 size_t occu_chain_smem(const Layout& L, int nstage, int block_threads);
 int occu_chain_block_threads(int ks, int ko);
+bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags);
+int occu_rn_chain_block_threads();
+size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D);
+cudaError_t launch_occu_rn_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
@@ -98,16 +102,32 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     if (!extra) pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit);
     pl.rn_scratch_off = (uint32_t)((pl.g.smem_bytes + 127) & ~size_t(127));
     pl.g.smem_bytes = pl.rn_scratch_off + extra;
-    pl.chain_kernel = ds->desc.model == BL_MODEL_OCCU && C >= kChainKernelMinChains && !ds->force_engine &&
-                      occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags);
+    const bool want_chain = C >= kChainKernelMinChains && !ds->force_engine;
+    pl.chain_kernel = 0;
+    if (want_chain && ds->desc.model == BL_MODEL_OCCU &&
+        occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
+      pl.chain_kernel = 1;
+    if (want_chain && C >= 128 && ds->desc.model == BL_MODEL_OCCU_RN &&
+        occu_rn_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags) &&
+        occu_rn_chain_smem(ds->L, 2, ds->desc.max_abundance, ds->D) <= ds->smem_limit)
+      pl.chain_kernel = 2;
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
-      const int bt = occu_chain_block_threads(ds->L.ks, ds->L.ko);  // chains per block
+      const int bt = pl.chain_kernel == 1 ? occu_chain_block_threads(ds->L.ks, ds->L.ko)
+                                          : occu_rn_chain_block_threads();  // chains per block
       pl.g.n_chunks = (C + bt - 1) / bt;
       pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
       pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
       pl.g.n_block_tiles = ds->L.n_tiles;
       pl.g.nstage = kMaxStages;
-      pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage, bt);
+      if (pl.chain_kernel == 1) {
+        pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage, bt);
+      } else {
+        while (pl.g.nstage > 2 &&
+               occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D) > ds->smem_limit)
+          --pl.g.nstage;
+        pl.g.smem_bytes = occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D);
+        pl.rn_global = false;
+      }
     }
     if (pl.g.smem_bytes > ds->smem_limit)
       return fail(BL_ERR_UNSUPPORTED, "shape needs %zu B of shared memory per block (> %zu)", pl.g.smem_bytes,
@@ -115,8 +135,9 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     EvalParams p;
     fill_params(ds, p);
     int occ = 0;
-    cudaError_t e = pl.chain_kernel ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
-                                    : launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
+    cudaError_t e = pl.chain_kernel == 1   ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                    : pl.chain_kernel == 2 ? launch_occu_rn_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                                           : launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
     if (e != cudaSuccess) return fail(BL_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (occ < 1) return fail(BL_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", pl.g.smem_bytes);
     pl.occupancy = occ;
@@ -189,8 +210,9 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.rn_scratch_off = pl->rn_scratch_off;
   p.rn_scratch_global = pl->rn_global ? ds->rn_scratch : nullptr;
   const dim3 grid(pl->g.nsplit, pl->g.n_chunks);
-  cudaError_t e = pl->chain_kernel ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
-                                   : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
+  cudaError_t e = pl->chain_kernel == 1   ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
+                  : pl->chain_kernel == 2 ? launch_occu_rn_chain(p, grid, pl->g.smem_bytes, st, nullptr)
+                                          : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
   if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (ds->comm) return comm_post_eval(ds, p, st);  // cross-rank sum of the raw sums, then priors

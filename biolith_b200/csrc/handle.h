@@ -11,7 +11,7 @@ struct Plan {
   int occupancy;
   uint32_t rn_scratch_off;
   bool rn_global;  // occu_rn A_k scratch lives in global memory
-  bool chain_kernel;  // lane = chain variant (occu_chain.cu) instead of the site-parallel engine
+  int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel; 2: occu_rn lane=chain kernel
 };
 }  // namespace bl
 

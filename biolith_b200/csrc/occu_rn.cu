@@ -21,6 +21,7 @@ namespace bl {
 
 constexpr int kMaxAbundance = 1023;
 __constant__ double c_lgamma[kMaxAbundance + 1];  // lgamma(k + 1)
+__constant__ float c_lgamma_f[kMaxAbundance + 1];
 
 template <typename T, int KS, int KO, bool STRICT>
 struct OccuRnModel {
@@ -227,6 +228,302 @@ struct OccuRnModel {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// K2c: chain-parallel Royle-Nichols kernel (fp32, SFU math, C >= 64): lane = chain, sites and their
+// detection / mask bits are warp-uniform.  Two consequences make it ~4x cheaper than the site-parallel
+// form above: (1) the y branch is uniform, so the expensive k-loop with log(P_k) runs only for visits
+// with a detection; (2) non-detections are linear in k, log(1-P_k) = k u_j + log(1-c), except where
+// the clamp binds (k u_j + log(1-c) <= log eps), so they are folded into one slope U = sum u_j plus a
+// short descending correction loop over the clamped tail states only.
+// ------------------------------------------------------------------------------------------------
+template <int KS, int KO, int BT>
+__global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p) {
+  using N = Num<float>;
+  using M = Mth<float, true>;
+  constexpr int KB = KS + 1, KA = KO + 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
+  __shared__ int s_is_last;
+  const int F = p.L.F, J = p.L.J, K = p.K, NQ = p.NQ, D = p.D;
+  const bool fpc = (p.flags & BL_FLAG_FP_CONSTANT) != 0;
+  const uint32_t tile_elems = (uint32_t)F * kWarp;
+  const uint32_t tile_bytes = tile_elems * sizeof(float);
+  float* yfx = stage0 + (size_t)p.nstage * tile_elems;
+  float* mfx = yfx + (size_t)J * kWarp;
+  const int tid = threadIdx.x;
+  double* g64 = reinterpret_cast<double*>(mfx + (size_t)J * kWarp) + tid;      // [NQ][BT]
+  float* A = reinterpret_cast<float*>(g64 - tid + (size_t)NQ * BT) + tid;      // [K+1][BT]
+  const int c0 = blockIdx.y * p.CB;
+  const int ncb = min(p.CB, p.C - c0);
+  const bool chain_ok = tid < ncb;
+  const int64_t nbt = p.n_block_tiles;
+  const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
+  const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
+  const int n_it = (int)(bt_end - bt_begin);
+  const float* packed = reinterpret_cast<const float*>(p.packed);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nstage; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  float b[KB], a[KA];
+  float l1mc = 0.f, cval = 0.f, omc = 1.f, dcdx = 0.f;
+  {
+    const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * D;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) b[k] = th[k];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) a[k] = th[KB + k];
+    if (fpc) {
+      const float x = th[D - 1];
+      cval = 1.f / (1.f + expf(-x));
+      l1mc = -(fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))));
+      omc = 1.f - cval;
+      dcdx = cval * omc;
+    }
+  }
+  for (int i = 0; i < NQ; ++i) g64[(size_t)i * BT] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    const int pre = min(p.nstage, n_it);
+    for (int s = 0; s < pre; ++s) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + s) * tile_elems, tile_bytes,
+                    &bars[s]);
+    }
+  }
+  const float log_eps = N::log_eps();
+
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it % p.nstage;
+    mbar_wait(&bars[s], (uint32_t)((it / p.nstage) & 1));
+    const float* tile = stage0 + (size_t)s * tile_elems;
+    const int64_t unit0 = (bt_begin + it) * kWarp;
+    const int n_valid = (int)max((int64_t)0, min((int64_t)kWarp, p.L.n_units - unit0));
+    for (int e = tid; e < J * kWarp; e += BT) {
+      const int site = e & 31, j = e >> 5;
+      const uint32_t yw = __float_as_uint(tile[(p.L.off_y + (j >> 5)) * kWarp + site]);
+      const uint32_t mw = __float_as_uint(tile[(p.L.off_m + (j >> 5)) * kWarp + site]);
+      yfx[e] = ((yw >> (j & 31)) & 1u) ? 1.f : 0.f;
+      mfx[e] = ((mw >> (j & 31)) & 1u) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    float acc_gb[KB], acc_ga[KA], acc_gc = 0.f;
+    double logp_tile = 0.0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) acc_gb[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) acc_ga[k] = 0.f;
+
+    for (int si = 0; si < n_valid; ++si) {
+      float x[KS > 0 ? KS : 1];
+      float eta = b[0];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        x[k] = tile[k * kWarp + si];
+        eta = fmaf(x[k], b[1 + k], eta);
+      }
+      // ---- prior logits k eta - lgamma(k+1) (the -lambda term cancels) and their normaliser
+      float Mp = -N::inf();
+#pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+        const float lk = fmaf((float)k, eta, -c_lgamma_f[k]);
+        A[(size_t)k * BT] = lk;
+        Mp = fmaxf(Mp, lk);
+      }
+      float Zp = 0.f, Ep = 0.f;
+#pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+        const float e = M::exp_(A[(size_t)k * BT] - Mp);
+        Zp += e;
+        Ep = fmaf((float)k, e, Ep);
+      }
+      const float logZp = Mp + M::log_(Zp);
+      Ep *= M::rcp_(Zp);
+      // ---- pass 1
+      float Utot = 0.f, n0 = 0.f;
+      for (int j = 0; j < J; ++j) {
+        if (mfx[j * kWarp + si] == 0.f) continue;  // warp-uniform
+        float nu = a[0];
+#pragma unroll
+        for (int k = 0; k < KO; ++k) nu = fmaf(tile[(p.L.off_w + j * KO + k) * kWarp + si], a[1 + k], nu);
+        float sp, r;
+        M::softsig(nu, sp, r);
+        const float u = -sp;
+        if (yfx[j * kWarp + si] == 0.f) {  // warp-uniform
+          Utot += u;
+          n0 += 1.f;
+          for (int k = K; k >= 0; --k) {  // clamped tail states only: replace k u + log(1-c) by log eps
+            const float lq = fmaf((float)k, u, l1mc);
+            if (lq > log_eps) break;
+            A[(size_t)k * BT] += log_eps - lq;
+          }
+        } else {
+          const float qv = 1.f - r;
+          float qk = 1.f, P0 = 0.f;
+    #pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+            const float lq = fmaf((float)k, u, l1mc);
+            const float P = fmaf(omc, P0, cval);
+            const bool lo = P <= -N::neg_tiny();
+            const bool hi = lq <= log_eps;
+            const float t = lo ? N::log_tiny() : (hi ? N::log1m_eps() : M::log_(P));
+            A[(size_t)k * BT] += t;
+            P0 = fmaf(qk, r, P0);
+            qk *= qv;
+          }
+        }
+      }
+      // ---- posterior over N (adds the linear non-detection part k U + n0 log(1-c))
+      const float off0 = n0 * l1mc;
+      float Mx = -N::inf();
+#pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+        const float v = A[(size_t)k * BT] + fmaf((float)k, Utot, off0);
+        A[(size_t)k * BT] = v;
+        Mx = fmaxf(Mx, v);
+      }
+      float Z = 0.f;
+#pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+        const float e = M::exp_(A[(size_t)k * BT] - Mx);
+        A[(size_t)k * BT] = e;
+        Z += e;
+      }
+      const float iZ = M::rcp_(Z);
+      float Eq = 0.f, Wsum = 0.f;
+#pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+        const float w = A[(size_t)k * BT] * iZ;
+        A[(size_t)k * BT] = w;
+        Eq = fmaf((float)k, w, Eq);
+        Wsum += w;
+      }
+      const float ell = (Mx + M::log_(Z)) - logZp;
+      const float geta = Eq - Ep;
+      // ---- pass 2
+      float ga0 = 0.f, gc = 0.f, ga[KO > 0 ? KO : 1];
+#pragma unroll
+      for (int k = 0; k < KO; ++k) ga[k] = 0.f;
+      for (int j = 0; j < J; ++j) {
+        if (mfx[j * kWarp + si] == 0.f) continue;
+        float w[KO > 0 ? KO : 1];
+        float nu = a[0];
+#pragma unroll
+        for (int k = 0; k < KO; ++k) {
+          w[k] = tile[(p.L.off_w + j * KO + k) * kWarp + si];
+          nu = fmaf(w[k], a[1 + k], nu);
+        }
+        float sp, r;
+        M::softsig(nu, sp, r);
+        const float u = -sp;
+        float g, gcj;
+        if (yfx[j * kWarp + si] == 0.f) {
+          float tk = 0.f, t0 = 0.f;  // weight (and k-weighted weight) of the clamped tail states
+          for (int k = K; k >= 0; --k) {
+            const float lq = fmaf((float)k, u, l1mc);
+            if (lq > log_eps) break;
+            const float wk = A[(size_t)k * BT];
+            tk = fmaf((float)k, wk, tk);
+            t0 += wk;
+          }
+          g = Eq - tk;
+          gcj = Wsum - t0;
+        } else {
+          const float qv = 1.f - r;
+          float qk = 1.f, P0 = 0.f;
+          g = 0.f; gcj = 0.f;
+    #pragma unroll 4
+      for (int k = 0; k <= K; ++k) {
+            const float lq = fmaf((float)k, u, l1mc);
+            const float P = fmaf(omc, P0, cval);
+            const bool inr = (P > -N::neg_tiny()) && (lq > log_eps);
+            const float dt = inr ? -(omc * qk) * M::rcp_(P) : 0.f;
+            const float wd = A[(size_t)k * BT] * dt;
+            g = fmaf((float)k, wd, g);
+            gcj += wd;
+            P0 = fmaf(qk, r, P0);
+            qk *= qv;
+          }
+        }
+        const float gnu = -r * g;
+        ga0 += gnu;
+#pragma unroll
+        for (int k = 0; k < KO; ++k) ga[k] = fmaf(gnu, w[k], ga[k]);
+        gc += gcj;
+      }
+      logp_tile += (double)ell;
+      acc_gb[0] += geta;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) acc_gb[1 + k] = fmaf(geta, x[k], acc_gb[1 + k]);
+      acc_ga[0] += ga0;
+#pragma unroll
+      for (int k = 0; k < KO; ++k) acc_ga[1 + k] += ga[k];
+      acc_gc += gc;
+    }
+    g64[0] += logp_tile;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) g64[(size_t)(1 + k) * BT] += (double)acc_gb[k];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) g64[(size_t)(1 + KB + k) * BT] += (double)acc_ga[k];
+    if (fpc) g64[(size_t)(1 + KB + KA) * BT] += (double)(-acc_gc * dcdx / omc);
+    __syncthreads();
+    if (tid == 0 && it + p.nstage < n_it) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + it + p.nstage) * tile_elems,
+                    tile_bytes, &bars[s]);
+    }
+  }
+  if (chain_ok) {
+    double* my = p.partial + ((size_t)blockIdx.x * p.C + c0 + tid) * NQ;
+    for (int i = 0; i < NQ; ++i) my[i] = g64[(size_t)i * BT];
+  }
+  finish_block<float>(p, c0, ncb, &s_is_last);
+}
+
+constexpr int kRnChainThreads = 256;
+
+bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
+  if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
+  return (ks == 1 && ko == 1) || (ks == 5 && ko == 3);
+}
+
+int occu_rn_chain_block_threads() { return kRnChainThreads; }
+
+size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D) {
+  size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
+  bts = (bts + 15) & ~size_t(15);
+  bts += (size_t)(1 + D) * kRnChainThreads * sizeof(double);
+  return bts + (size_t)(K + 1) * kRnChainThreads * sizeof(float);
+}
+
+template <int KS, int KO>
+static cudaError_t launch_rn_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  auto kern = occu_rn_chain_kernel<KS, KO, kRnChainThreads>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kRnChainThreads, smem);
+  kern<<<grid, kRnChainThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t ensure_lgamma_table();
+
+cudaError_t launch_occu_rn_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  if (!occ) {
+    cudaError_t e = ensure_lgamma_table();
+    if (e != cudaSuccess) return e;
+  }
+  if (p.L.ks == 1 && p.L.ko == 1) return launch_rn_chain_one<1, 1>(p, grid, smem, st, occ);
+  if (p.L.ks == 5 && p.L.ko == 3) return launch_rn_chain_one<5, 3>(p, grid, smem, st, occ);
+  return cudaErrorNotSupported;
+}
+
 template <typename T, int KS, int KO, bool STRICT>
 static cudaError_t launch_rn_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t stream, int* occ) {
   auto kern = eval_kernel<T, OccuRnModel<T, KS, KO, STRICT>, 1>;
@@ -252,6 +549,11 @@ static cudaError_t ensure_lgamma_table() {
   double h[kMaxAbundance + 1];
   for (int k = 0; k <= kMaxAbundance; ++k) h[k] = std::lgamma((double)k + 1.0);
   status = cudaMemcpyToSymbol(c_lgamma, h, sizeof(h));
+  if (status == cudaSuccess) {
+    static float hf[kMaxAbundance + 1];
+    for (int k = 0; k <= kMaxAbundance; ++k) hf[k] = (float)h[k];
+    status = cudaMemcpyToSymbol(c_lgamma_f, hf, sizeof(hf));
+  }
   if (status == cudaSuccess && dev < 64) done[dev] = true;
   (void)once;
   return status;

@@ -208,11 +208,38 @@ def test_strict_math_flag(name):
     """BL_FLAG_STRICT_MATH (libm expf/log1pf/IEEE division) and the default bounded-error SFU forms
     both meet the fp32 tolerance; their mutual difference is at fp32-rounding level."""
     g = load_golden(name)
-    th = np.tile(g["thetas"], (12, 1))  # 84 chains -> the chain-parallel kernel where it exists
-    ref_lp = np.tile(g["logp_f32"], 12)
-    ref_gr = np.tile(g["grad_f32"], (12, 1))
+    th = np.tile(g["thetas"], (20, 1))  # 140 chains -> the chain-parallel kernels where they exist
+    ref_lp = np.tile(g["logp_f32"], 20)
+    ref_gr = np.tile(g["grad_f32"], (20, 1))
     with _make(g, "float32", strict_math=True) as strict, _make(g, "float32") as fast:
         lp_s, gr_s = strict.logp_and_grad(th)
         lp_f, gr_f = fast.logp_and_grad(th)
     assert_close(lp_s, gr_s, ref_lp, ref_gr, 1e-5, f"{name}/strict")
     assert_close(lp_f, gr_f, ref_lp, ref_gr, 1e-5, f"{name}/sfu")
+
+
+@pytest.mark.parametrize("ks,ko,K,fpc", [(1, 1, 100, False), (5, 3, 50, False), (5, 3, 30, True), (1, 1, 12, True)])
+def test_rn_chain_kernel_against_oracle(ks, ko, K, fpc):
+    """The lane=chain Royle-Nichols kernel (C >= 64): ragged visits, NaN covariates, clamp-active
+    states (r close to 1 makes k*log(1-r) cross log eps), optional false-positive constant."""
+    import biolith_b200 as bb
+    from oracle import occupancy as orc
+
+    rng = np.random.default_rng(K + ks)
+    S, J = 157, 11
+    X = rng.normal(size=(S, ks))
+    W = rng.normal(size=(S, 1, J, ko)) * 1.5
+    y = (rng.uniform(size=(1, S, 1, J)) < 0.3).astype(float)
+    lens = rng.integers(0, J + 1, size=S)
+    y[0, :, 0][np.arange(J)[None, :] >= lens[:, None]] = np.nan
+    W[rng.uniform(size=W.shape) < 0.03] = np.nan
+    D = ks + ko + 2 + int(fpc)
+    th = rng.uniform(-2, 2, size=(150, D))
+    pr = orc.prepare(X, W, y)
+    idx = [0, 1, 33, 149]
+    ref_lp, ref_gr = orc.logp_grad("occu_rn", th[idx], pr, max_abundance=K, fp_constant=fpc)
+    with bb.OccupancyLikelihood("occu_rn", X, W, y, max_abundance=K, false_positives_constant=fpc) as lk:
+        lp, gr = lk.logp_and_grad(th)
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"rn chain ks={ks} K={K} fpc={fpc}")
+        lp_e, gr_e = lk.logp_and_grad(th[:8])  # same handle, site-parallel engine (C < 64)
+        np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
