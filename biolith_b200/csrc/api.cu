@@ -45,11 +45,15 @@ bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 int occu_rn_chain_block_threads();
 size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D);
 cudaError_t launch_occu_rn_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
+bool occu_cop_chain_supported(int dtype, int ks, int ko, uint32_t flags);
+int occu_cop_chain_block_threads();
+size_t occu_cop_chain_smem(const Layout& L, int nstage);
+cudaError_t launch_occu_cop_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
 
-constexpr int kChainKernelMinChains = 64;
+constexpr int kChainKernelMinChains = 128;  // below this a 256-thread chain block is mostly idle lanes
 
 static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st,
                                 int* occ) {
@@ -107,13 +111,17 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     if (want_chain && ds->desc.model == BL_MODEL_OCCU &&
         occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
       pl.chain_kernel = 1;
-    if (want_chain && C >= 128 && ds->desc.model == BL_MODEL_OCCU_RN &&
+    if (want_chain && ds->desc.model == BL_MODEL_OCCU_RN &&
         occu_rn_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags) &&
         occu_rn_chain_smem(ds->L, 2, ds->desc.max_abundance, ds->D) <= ds->smem_limit)
       pl.chain_kernel = 2;
+    if (want_chain && ds->desc.model == BL_MODEL_OCCU_COP &&
+        occu_cop_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
+      pl.chain_kernel = 3;
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
-      const int bt = pl.chain_kernel == 1 ? occu_chain_block_threads(ds->L.ks, ds->L.ko)
-                                          : occu_rn_chain_block_threads();  // chains per block
+      const int bt = pl.chain_kernel == 1   ? occu_chain_block_threads(ds->L.ks, ds->L.ko)
+                     : pl.chain_kernel == 2 ? occu_rn_chain_block_threads()
+                                            : occu_cop_chain_block_threads();  // chains per block
       pl.g.n_chunks = (C + bt - 1) / bt;
       pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
       pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
@@ -121,6 +129,8 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       pl.g.nstage = kMaxStages;
       if (pl.chain_kernel == 1) {
         pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage, bt);
+      } else if (pl.chain_kernel == 3) {
+        pl.g.smem_bytes = occu_cop_chain_smem(ds->L, pl.g.nstage);
       } else {
         while (pl.g.nstage > 2 &&
                occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D) > ds->smem_limit)
@@ -137,6 +147,7 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     int occ = 0;
     cudaError_t e = pl.chain_kernel == 1   ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 2 ? launch_occu_rn_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                    : pl.chain_kernel == 3 ? launch_occu_cop_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                                            : launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
     if (e != cudaSuccess) return fail(BL_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (occ < 1) return fail(BL_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", pl.g.smem_bytes);
@@ -212,6 +223,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   const dim3 grid(pl->g.nsplit, pl->g.n_chunks);
   cudaError_t e = pl->chain_kernel == 1   ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 2 ? launch_occu_rn_chain(p, grid, pl->g.smem_bytes, st, nullptr)
+                  : pl->chain_kernel == 3 ? launch_occu_cop_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                                           : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
   if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -142,6 +142,221 @@ struct OccuCopModel {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// K3c: chain-parallel count-detection kernel (fp32, SFU math, C >= 64).  Same mapping as K1c
+// (occu_chain.cu): lane = chain with theta and the running sums in registers, sites warp-broadcast, 4
+// consecutive sites per LDS.128.  Masked visits are packed as (y, T) = (0, 0) and vanish on their own,
+// so the loop has no mask handling at all; per visit: exp (ex2), log (lg2) and reciprocal (rcp) of the
+// rate -> 3 MUFU like the Bernoulli kernel.
+// ------------------------------------------------------------------------------------------------
+template <int KS, int KO, int BT, int JT>
+__global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams p) {
+  constexpr int KB = KS + 1, KA = KO + 1, NS = 4, NQM = 1 + KB + KA + 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
+  __shared__ int s_is_last;
+  const int F = p.L.F, J = JT > 0 ? JT : p.L.J, NQ = p.NQ, D = p.D;
+  const uint32_t tile_elems = (uint32_t)F * kWarp;
+  const uint32_t tile_bytes = tile_elems * sizeof(float);
+  const int tid = threadIdx.x;
+  double* g64 = reinterpret_cast<double*>(stage0 + (size_t)p.nstage * tile_elems) + tid;  // [NQM][BT]
+  const int c0 = blockIdx.y * p.CB;
+  const int ncb = min(p.CB, p.C - c0);
+  const bool chain_ok = tid < ncb;
+  const int64_t nbt = p.n_block_tiles;
+  const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
+  const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
+  const int n_it = (int)(bt_end - bt_begin);
+  const float* packed = reinterpret_cast<const float*>(p.packed);
+  const bool fpc = (p.flags & BL_FLAG_FP_CONSTANT) != 0, fpu = (p.flags & BL_FLAG_FP_UNOCCUPIED) != 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nstage; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  float b[KB], a[KA];
+  float c = 0.f, u = 0.f;
+  {
+    const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * D;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) b[k] = th[k];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) a[k] = th[KB + k];
+    int i = KB + KA;
+    if (fpc) c = expf(th[i++]);
+    if (fpu) u = expf(th[i++]);
+  }
+  const float rho0 = u + c;
+  const float lrho0 = rho0 > 0.f ? logf(rho0) : -Num<float>::inf();
+  const float irho0 = rho0 > 0.f ? 1.f / rho0 : 0.f;
+  double logp64 = 0.0;
+#pragma unroll
+  for (int i = 1; i < NQM; ++i) g64[(size_t)i * BT] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    const int pre = min(p.nstage, n_it);
+    for (int s = 0; s < pre; ++s) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + s) * tile_elems, tile_bytes,
+                    &bars[s]);
+    }
+  }
+
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it % p.nstage;
+    mbar_wait(&bars[s], (uint32_t)((it / p.nstage) & 1));
+    const float* tile = stage0 + (size_t)s * tile_elems;
+    const int64_t unit0 = (bt_begin + it) * kWarp;
+    const int n_valid = (int)max((int64_t)0, min((int64_t)kWarp, p.L.n_units - unit0));
+    float acc[NQM];
+#pragma unroll
+    for (int i = 0; i < NQM; ++i) acc[i] = 0.f;
+    for (int g0 = 0; g0 < n_valid; g0 += NS) {
+      float x[KS > 0 ? KS : 1][NS], eta[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) eta[i] = b[0];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + k * kWarp + g0);
+        x[k][0] = v.x; x[k][1] = v.y; x[k][2] = v.z; x[k][3] = v.w;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) eta[i] = fmaf(x[k][i], b[1 + k], eta[i]);
+      }
+      float L1[NS], s1[NS], ga0[NS], ga[KO > 0 ? KO : 1][NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        L1[i] = 0.f; s1[i] = 0.f; ga0[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KO; ++k) ga[k][i] = 0.f;
+      }
+#pragma unroll(JT > 0 ? JT : 2)
+      for (int j = 0; j < J; ++j) {
+        float w[KO > 0 ? KO : 1][NS], nu[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) nu[i] = a[0];
+#pragma unroll
+        for (int k = 0; k < KO; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(tile + (p.L.off_w + j * KO + k) * kWarp + g0);
+          w[k][0] = v.x; w[k][1] = v.y; w[k][2] = v.z; w[k][3] = v.w;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) nu[i] = fmaf(w[k][i], a[1 + k], nu[i]);
+        }
+        const float4 yv = *reinterpret_cast<const float4*>(tile + (p.L.off_y + j) * kWarp + g0);
+        const float4 tv = *reinterpret_cast<const float4*>(tile + (p.L.off_t + j) * kWarp + g0);
+        const float y[NS] = {yv.x, yv.y, yv.z, yv.w}, T[NS] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          const float mu = sfu::ex2(nu[i] * sfu::kLog2e);
+          const float rho1 = mu + c;
+          const bool ypos = y[i] > 0.f;
+          const float ylog = ypos ? (y[i] * sfu::kLn2) * sfu::lg2(rho1) : 0.f;  // xlogy(y, rho1)
+          const float yinv = ypos ? y[i] * sfu::rcp(rho1) : 0.f;
+          L1[i] += fmaf(-T[i], rho1, ylog);
+          const float d1 = yinv - T[i];  // dt1/drho1
+          s1[i] += d1;
+          const float g = d1 * mu;       // drho1/dnu = mu
+          ga0[i] += g;
+#pragma unroll
+          for (int k = 0; k < KO; ++k) ga[k][i] = fmaf(g, w[k][i], ga[k][i]);
+        }
+      }
+      const float4 syv = *reinterpret_cast<const float4*>(tile + p.L.off_sy * kWarp + g0);
+      const float4 stv = *reinterpret_cast<const float4*>(tile + (p.L.off_sy + 1) * kWarp + g0);
+      const float sy[NS] = {syv.x, syv.y, syv.z, syv.w}, st[NS] = {stv.x, stv.y, stv.z, stv.w};
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const float vf = (g0 + i < n_valid) ? 1.f : 0.f;
+        const float L0 = (sy[i] > 0.f ? sy[i] * lrho0 : 0.f) - st[i] * rho0;
+        const float d0 = (sy[i] > 0.f ? sy[i] * irho0 : 0.f) - st[i];
+        const sfu::SoftSig se = sfu::softsig<true>(eta[i]);
+        const float av = (se.xc - se.s) + L1[i];
+        const float bv = L0 - se.s;
+        float rr, ell;
+        if (bv == -Num<float>::inf()) {  // Poisson(0) saw a count: occupied with certainty
+          rr = 1.f;
+          ell = av;
+        } else {
+          const float d = av - bv;
+          const float td = sfu::ex2(-fabsf(d) * sfu::kLog2e);
+          const float ud = 1.0f + td;
+          const float invd = sfu::rcp(ud);
+          rr = (d >= 0.f) ? invd : td * invd;
+          ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv));
+        }
+        const float r = rr * vf;
+        const float geta = se.inr ? (rr - se.p) * vf : 0.f;
+        const float w0 = (rr < 1.f) ? (1.f - rr) * d0 * vf : 0.f;
+        logp64 += (double)(ell * vf);
+        acc[1] += geta;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[2 + k] = fmaf(geta, x[k][i], acc[2 + k]);
+        acc[1 + KB] = fmaf(r, ga0[i], acc[1 + KB]);
+#pragma unroll
+        for (int k = 0; k < KO; ++k) acc[2 + KB + k] = fmaf(r, ga[k][i], acc[2 + KB + k]);
+        acc[1 + KB + KA] += fmaf(r, s1[i], w0);  // dl/dc (constant fp): both branches
+        acc[2 + KB + KA] += w0;                  // dl/du (unoccupied fp): z = 0 branch only
+      }
+    }
+#pragma unroll
+    for (int i = 1; i < NQM; ++i) g64[(size_t)i * BT] += (double)acc[i];
+    __syncthreads();
+    if (tid == 0 && it + p.nstage < n_it) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + it + p.nstage) * tile_elems,
+                    tile_bytes, &bars[s]);
+    }
+  }
+  if (chain_ok) {
+    double* my = p.partial + ((size_t)blockIdx.x * p.C + c0 + tid) * NQ;
+    my[0] = logp64;
+    for (int i = 1; i < 1 + KB + KA; ++i) my[i] = g64[(size_t)i * BT];
+    int i = 1 + KB + KA;
+    const double gc = g64[(size_t)(1 + KB + KA) * BT], gu = g64[(size_t)(2 + KB + KA) * BT];
+    if (fpc) my[i++] = gc * (double)c;  // x = log c: dc/dx = c
+    if (fpu) my[i++] = gu * (double)u;
+  }
+  finish_block<float>(p, c0, ncb, &s_is_last);
+}
+
+constexpr int kCopChainThreads = 256;
+
+bool occu_cop_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
+  if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
+  return (ks == 1 && ko == 1) || (ks == 5 && ko == 3);
+}
+
+int occu_cop_chain_block_threads() { return kCopChainThreads; }
+
+size_t occu_cop_chain_smem(const Layout& L, int nstage) {
+  size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float);
+  bts = (bts + 15) & ~size_t(15);
+  return bts + (size_t)(5 + L.ks + L.ko) * kCopChainThreads * sizeof(double);
+}
+
+template <int KS, int KO, int JT>
+static cudaError_t launch_cop_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  auto kern = occu_cop_chain_kernel<KS, KO, kCopChainThreads, JT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kCopChainThreads, smem);
+  kern<<<grid, kCopChainThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_occu_cop_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  if (p.L.ks == 1 && p.L.ko == 1) return launch_cop_chain_one<1, 1, 0>(p, grid, smem, st, occ);
+  if (p.L.ks == 5 && p.L.ko == 3) {
+    if (p.L.J == 12) return launch_cop_chain_one<5, 3, 12>(p, grid, smem, st, occ);
+    return launch_cop_chain_one<5, 3, 0>(p, grid, smem, st, occ);
+  }
+  return cudaErrorNotSupported;
+}
+
 template <typename T, int KS, int KO, bool STRICT>
 static cudaError_t launch_cop_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t stream, int* occ) {
   auto kern = eval_kernel<T, OccuCopModel<T, KS, KO, STRICT>, 2>;

@@ -54,7 +54,7 @@ def test_golden_parity(name, dtype):
         assert_close(lp, gr, g[f"loglik_{mode}"], g[f"gradlik_{mode}"], RTOL[dtype], f"{name}/{dtype}/lik")
 
 
-@pytest.mark.parametrize("n_chains", [1, 2, 3, 5, 8, 31, 64, 257, 700])
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 5, 8, 31, 64, 127, 128, 257, 700])
 def test_chain_batching_is_consistent(n_chains):
     """Every (C -> WS x WC arrangement, chunking) must give the same per-chain numbers."""
     from oracle import occupancy as orc
@@ -242,4 +242,34 @@ def test_rn_chain_kernel_against_oracle(ks, ko, K, fpc):
         lp, gr = lk.logp_and_grad(th)
         assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"rn chain ks={ks} K={K} fpc={fpc}")
         lp_e, gr_e = lk.logp_and_grad(th[:8])  # same handle, site-parallel engine (C < 64)
+        np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
+
+
+@pytest.mark.parametrize("ks,ko,fpc,fpu", [(1, 1, True, False), (5, 3, True, True), (5, 3, False, False), (1, 1, False, True)])
+def test_cop_chain_kernel_against_oracle(ks, ko, fpc, fpu):
+    """The lane=chain count-detection kernel (C >= 64): ragged / missing visits, varying exposure, every
+    false-positive configuration (without any, a unit that saw a count is occupied with certainty)."""
+    import biolith_b200 as bb
+    from oracle import occupancy as orc
+
+    rng = np.random.default_rng(ks * 10 + ko + int(fpc) + 2 * int(fpu))
+    S, J = 203, 12 if ks == 5 else 7
+    X = rng.normal(size=(S, ks))
+    W = rng.normal(size=(S, 1, J, ko)) * 0.7
+    y = rng.poisson(1.5, size=(1, S, 1, J)).astype(float)
+    y[0, rng.uniform(size=S) < 0.3] = 0.0  # sites without any count
+    lens = rng.integers(0, J + 1, size=S)
+    y[0, :, 0][np.arange(J)[None, :] >= lens[:, None]] = np.nan
+    W[rng.uniform(size=W.shape) < 0.03] = np.nan
+    T = rng.uniform(0.5, 9.0, size=(S, 1, J))
+    D = ks + ko + 2 + int(fpc) + int(fpu)
+    th = rng.uniform(-1.5, 1.5, size=(130, D))
+    pr = orc.prepare(X, W, y, T)
+    idx = [0, 1, 50, 129]
+    ref_lp, ref_gr = orc.logp_grad("occu_cop", th[idx], pr, fp_constant=fpc, fp_unoccupied=fpu)
+    with bb.OccupancyLikelihood("occu_cop", X, W, y, T, false_positives_constant=fpc,
+                                false_positives_unoccupied=fpu) as lk:
+        lp, gr = lk.logp_and_grad(th)
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"cop chain ks={ks} fpc={fpc} fpu={fpu}")
+        lp_e, gr_e = lk.logp_and_grad(th[:8])  # site-parallel engine on the same handle
         np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
