@@ -324,20 +324,25 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         x[k] = tile[k * kWarp + si];
         eta = fmaf(x[k], b[1 + k], eta);
       }
-      // ---- prior logits k eta - lgamma(k+1) (the -lambda term cancels) and their normaliser
-      float Mp = -N::inf();
-#pragma unroll 4
-      for (int k = 0; k <= K; ++k) {
-        const float lk = fmaf((float)k, eta, -c_lgamma_f[k]);
-        A[(size_t)k * BT] = lk;
-        Mp = fmaxf(Mp, lk);
+      // ---- prior logits k eta - lgamma(k+1) (the -lambda term cancels) and their normaliser.  The
+      // sequence is concave in k with its maximum at floor(lambda) or the next integer, so the shift of
+      // the log-sum-exp is known up front and one pass suffices.
+      float Mp;
+      {
+        const float lam = M::exp_(fminf(eta, 80.f));
+        const int k0 = (int)fminf(lam, (float)K);
+        const int k1 = min(k0 + 1, K);
+        Mp = fmaxf(fmaf((float)k0, eta, -c_lgamma_f[k0]), fmaf((float)k1, eta, -c_lgamma_f[k1]));
       }
-      float Zp = 0.f, Ep = 0.f;
+      float Zp = 0.f, Ep = 0.f, kf = 0.f;
 #pragma unroll 4
       for (int k = 0; k <= K; ++k) {
-        const float e = M::exp_(A[(size_t)k * BT] - Mp);
+        const float lk = fmaf(kf, eta, -c_lgamma_f[k]);
+        A[(size_t)k * BT] = lk;
+        const float e = M::exp_(lk - Mp);
         Zp += e;
-        Ep = fmaf((float)k, e, Ep);
+        Ep = fmaf(kf, e, Ep);
+        kf += 1.f;
       }
       const float logZp = Mp + M::log_(Zp);
       Ep *= M::rcp_(Zp);
@@ -354,55 +359,56 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         if (yfx[j * kWarp + si] == 0.f) {  // warp-uniform
           Utot += u;
           n0 += 1.f;
+          float kd = (float)K;
           for (int k = K; k >= 0; --k) {  // clamped tail states only: replace k u + log(1-c) by log eps
-            const float lq = fmaf((float)k, u, l1mc);
+            const float lq = fmaf(kd, u, l1mc);
             if (lq > log_eps) break;
             A[(size_t)k * BT] += log_eps - lq;
+            kd -= 1.f;
           }
         } else {
           const float qv = 1.f - r;
-          float qk = 1.f, P0 = 0.f;
-    #pragma unroll 4
-      for (int k = 0; k <= K; ++k) {
-            const float lq = fmaf((float)k, u, l1mc);
+          float qk = 1.f, P0 = 0.f, kk = 0.f;
+#pragma unroll 4
+          for (int k = 0; k <= K; ++k) {
+            const float lq = fmaf(kk, u, l1mc);
             const float P = fmaf(omc, P0, cval);
-            const bool lo = P <= -N::neg_tiny();
-            const bool hi = lq <= log_eps;
-            const float t = lo ? N::log_tiny() : (hi ? N::log1m_eps() : M::log_(P));
+            float t = M::log_(P);
+            t = (lq <= log_eps) ? N::log1m_eps() : t;
+            t = (P <= -N::neg_tiny()) ? N::log_tiny() : t;
             A[(size_t)k * BT] += t;
             P0 = fmaf(qk, r, P0);
             qk *= qv;
+            kk += 1.f;
           }
         }
       }
-      // ---- posterior over N (adds the linear non-detection part k U + n0 log(1-c))
+      // ---- posterior over N (adds the linear non-detection part k U + n0 log(1-c)); the weights stay
+      // unnormalised (e_k = exp(A_k - max)) and the sums are scaled by 1/Z afterwards
       const float off0 = n0 * l1mc;
       float Mx = -N::inf();
+      kf = 0.f;
 #pragma unroll 4
       for (int k = 0; k <= K; ++k) {
-        const float v = A[(size_t)k * BT] + fmaf((float)k, Utot, off0);
+        const float v = A[(size_t)k * BT] + fmaf(kf, Utot, off0);
         A[(size_t)k * BT] = v;
         Mx = fmaxf(Mx, v);
+        kf += 1.f;
       }
-      float Z = 0.f;
+      float Z = 0.f, Eqn = 0.f;
+      kf = 0.f;
 #pragma unroll 4
       for (int k = 0; k <= K; ++k) {
         const float e = M::exp_(A[(size_t)k * BT] - Mx);
         A[(size_t)k * BT] = e;
         Z += e;
+        Eqn = fmaf(kf, e, Eqn);
+        kf += 1.f;
       }
       const float iZ = M::rcp_(Z);
-      float Eq = 0.f, Wsum = 0.f;
-#pragma unroll 4
-      for (int k = 0; k <= K; ++k) {
-        const float w = A[(size_t)k * BT] * iZ;
-        A[(size_t)k * BT] = w;
-        Eq = fmaf((float)k, w, Eq);
-        Wsum += w;
-      }
       const float ell = (Mx + M::log_(Z)) - logZp;
-      const float geta = Eq - Ep;
-      // ---- pass 2
+      const float geta = Eqn * iZ - Ep;
+      // ---- pass 2 (sums over the unnormalised weights, scaled by 1/Z per visit)
       float ga0 = 0.f, gc = 0.f, ga[KO > 0 ? KO : 1];
 #pragma unroll
       for (int k = 0; k < KO; ++k) ga[k] = 0.f;
@@ -420,38 +426,41 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         const float u = -sp;
         float g, gcj;
         if (yfx[j * kWarp + si] == 0.f) {
-          float tk = 0.f, t0 = 0.f;  // weight (and k-weighted weight) of the clamped tail states
+          float tk = 0.f, t0 = 0.f, kd = (float)K;  // (k-weighted) weight of the clamped tail states
           for (int k = K; k >= 0; --k) {
-            const float lq = fmaf((float)k, u, l1mc);
+            const float lq = fmaf(kd, u, l1mc);
             if (lq > log_eps) break;
             const float wk = A[(size_t)k * BT];
-            tk = fmaf((float)k, wk, tk);
+            tk = fmaf(kd, wk, tk);
             t0 += wk;
+            kd -= 1.f;
           }
-          g = Eq - tk;
-          gcj = Wsum - t0;
+          g = Eqn - tk;
+          gcj = Z - t0;
         } else {
           const float qv = 1.f - r;
-          float qk = 1.f, P0 = 0.f;
+          float qk = 1.f, P0 = 0.f, kk = 0.f;
           g = 0.f; gcj = 0.f;
-    #pragma unroll 4
-      for (int k = 0; k <= K; ++k) {
-            const float lq = fmaf((float)k, u, l1mc);
+#pragma unroll 4
+          for (int k = 0; k <= K; ++k) {
+            const float lq = fmaf(kk, u, l1mc);
             const float P = fmaf(omc, P0, cval);
             const bool inr = (P > -N::neg_tiny()) && (lq > log_eps);
-            const float dt = inr ? -(omc * qk) * M::rcp_(P) : 0.f;
+            float dt = -(omc * qk) * M::rcp_(P);  // dt/dlq = -(1-P)/P, 1-P = (1-c) q^k
+            dt = inr ? dt : 0.f;
             const float wd = A[(size_t)k * BT] * dt;
-            g = fmaf((float)k, wd, g);
+            g = fmaf(kk, wd, g);
             gcj += wd;
             P0 = fmaf(qk, r, P0);
             qk *= qv;
+            kk += 1.f;
           }
         }
-        const float gnu = -r * g;
+        const float gnu = -r * g * iZ;  // dlq/dnu = -k r
         ga0 += gnu;
 #pragma unroll
         for (int k = 0; k < KO; ++k) ga[k] = fmaf(gnu, w[k], ga[k]);
-        gc += gcj;
+        gc = fmaf(gcj, iZ, gc);
       }
       logp_tile += (double)ell;
       acc_gb[0] += geta;
