@@ -15,6 +15,7 @@
 // Random numbers: Philox4x32-10 keyed by (seed, chain); statistically, not bitwise, equal to
 // numpyro's threefry streams.  Energies and the tree weights are fp64 (a 1M-site log-density is
 // ~1e6 in magnitude: fp32 would leave delta-energy a resolution of 0.5).
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -48,6 +49,7 @@ struct NutsParams {
   unsigned char* stat_div;  // [num_samples][C]
   double* stat_pe;    // [num_samples][C]
   int* n_done;        // [1]
+  int* slot;          // [C] row of chain c in the theta / logp / grad batch (finished chains are compacted away)
 };
 
 // vector fields ([D] each)
@@ -148,7 +150,7 @@ __device__ void set_next_leaf(const ChainView& cv) {
   const int fg = sub ? (right ? V_SGR : V_SGL) : (right ? V_GR : V_GL);
   const double de = right ? cv.s(S_EPS) : -cv.s(S_EPS);
   cv.s(S_DIREPS) = de;
-  T* th = reinterpret_cast<T*>(p.theta) + (size_t)cv.c * p.D;
+  T* th = reinterpret_cast<T*>(p.theta) + (size_t)p.slot[cv.c] * p.D;
   for (int d = 0; d < p.D; ++d) {
     const double rh = cv.v(fr, d) + 0.5 * de * cv.v(fg, d);  // r - (eps/2) dU/dz, dU = -dlogp
     const double zn = cv.v(fz, d) + de * cv.v(V_IMM, d) * rh;
@@ -252,6 +254,7 @@ __global__ void nuts_start_kernel(NutsParams p) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
   ChainView cv{p, c};
+  p.slot[c] = c;
   Philox rng{(unsigned int)p.seed, (unsigned int)(p.seed >> 32), (unsigned int)c, 0x6e757473u, 0ull};
   const T* th = reinterpret_cast<const T*>(p.theta) + (size_t)c * p.D;
   const T* gr = reinterpret_cast<const T*>(p.grad) + (size_t)c * p.D;
@@ -288,9 +291,10 @@ __global__ void nuts_advance_kernel(NutsParams p) {
   if (warm) cv.i(I_LEAPS_WARM) += 1;
 
   // ---- 1. finish the leapfrog at z_new, build the leaf (numpyro _build_basetree)
-  const T* gr = reinterpret_cast<const T*>(p.grad) + (size_t)c * D;
+  const int row = p.slot[c];
+  const T* gr = reinterpret_cast<const T*>(p.grad) + (size_t)row * D;
   const double de = cv.s(S_DIREPS);
-  const double U_new = -p.logp[c];
+  const double U_new = -p.logp[row];
   double kin = 0.0;
   // r_new is written straight into the subtree's outer edge slot after the combine decision;
   // stage it in V_RHALF (in place)
@@ -426,6 +430,40 @@ __global__ void nuts_advance_kernel(NutsParams p) {
   cv.i(I_CTR_HI) = (int)(unsigned int)(rng.ctr >> 32);
 }
 
+// Re-number the rows of the evaluation batch so that the still-running chains are contiguous (one
+// block; order-preserving, hence identical on every rank of a site-sharded run) and re-emit their
+// pending positions into the new rows.
+template <typename T>
+__global__ void nuts_compact_kernel(NutsParams p) {
+  __shared__ int s_base;
+  __shared__ int s_warp[32];
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c0 = 0; c0 < p.C; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    const int active = (c < p.C && !p.isc[(size_t)I_DONE * p.C + c]) ? 1 : 0;
+    const unsigned int m = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int row = before + __popc(m & ((1u << lane) - 1u));
+    if (active) {
+      p.slot[c] = row;
+      T* th = reinterpret_cast<T*>(p.theta) + (size_t)row * p.D;
+      for (int d = 0; d < p.D; ++d) th[d] = (T)p.vec[((size_t)V_ZNEW * p.D + d) * p.C + c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < nwarp; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace bl
 
 using namespace bl;
@@ -442,6 +480,8 @@ struct bl_nuts {
   // CUDA graph of `graph_steps` x (eval + advance): the inner loop is launch-bound on small datasets
   cudaGraphExec_t graph_exec = nullptr;
   int graph_steps = 0;
+  int n_rows = 0;          // current evaluation batch (active chains rounded up to a chain chunk)
+  bool compaction = true;
 };
 
 // numpyro build_adaptation_schedule (hmc_util.py): Stan's 75 / 25*2^k / 50 windows
@@ -482,7 +522,7 @@ int bl_nuts_destroy(bl_nuts* s) {
   cudaFree(s->p.vec); cudaFree(s->p.sc); cudaFree(s->p.isc); cudaFree(s->p.ckpt); cudaFree(s->p.theta);
   cudaFree(s->d_grad); cudaFree(s->d_logp_t); cudaFree(s->d_logp64); cudaFree(s->p.samples);
   cudaFree(s->p.stat_accept); cudaFree(s->p.stat_steps); cudaFree(s->p.stat_div); cudaFree(s->p.stat_pe);
-  cudaFree(s->p.n_done);
+  cudaFree(s->p.n_done); cudaFree(s->p.slot);
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -534,6 +574,7 @@ int bl_nuts_create(bl_dataset* ds, const bl_nuts_config* cfg, const void* theta0
   CU_NB(cudaMalloc(&p.stat_div, N * C));
   CU_NB(cudaMalloc(&p.stat_pe, N * C * sizeof(double)));
   CU_NB(cudaMalloc(&p.n_done, sizeof(int)));
+  CU_NB(cudaMalloc(&p.slot, C * sizeof(int)));
   CU_NB(cudaMemset(p.n_done, 0, sizeof(int)));
   CU_NB(cudaMemset(p.isc, 0, (size_t)I_COUNT * C * sizeof(int)));
   CU_NB(cudaMemset(p.vec, 0, (size_t)V_COUNT * D * C * sizeof(double)));
@@ -545,6 +586,7 @@ int bl_nuts_create(bl_dataset* ds, const bl_nuts_config* cfg, const void* theta0
   if (rc != BL_OK) { bl_nuts_destroy(s); return rc; }
   p.grad = s->d_grad;
   p.logp = s->d_logp64;
+  s->n_rows = p.C;
   *out = s;
   return BL_OK;
 }
@@ -569,17 +611,19 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
     s->started = true;
   }
   auto one_step = [&]() -> int {
-    int rc = eval_device(ds, p.theta, p.C, s->d_logp_t, s->d_grad, s->stream, 0, s->d_logp64);
+    int rc = eval_device(ds, p.theta, s->n_rows, s->d_logp_t, s->d_grad, s->stream, 0, s->d_logp64);
     if (rc) return rc;
     if (f32) nuts_advance_kernel<float><<<blocks, threads, 0, s->stream>>>(p);
     else nuts_advance_kernel<double><<<blocks, threads, 0, s->stream>>>(p);
     g_launches.fetch_add(1);
     return BL_OK;
   };
-  // Capture poll_every x (eval + advance) once and replay it (not with a cross-rank exchange attached:
-  // the P2P epoch is a kernel argument).  The plan / workspace already exist (the start eval ran).
-  if (!ds->comm && !s->graph_exec && max_steps >= poll_every && s->graph_steps == 0) {
-    s->graph_steps = -1;  // do not retry if capture is refused
+  // Capture poll_every x (eval + advance) and replay it (not with a cross-rank exchange attached: the
+  // P2P epoch is a kernel argument).  Re-captured whenever compaction shrinks the batch.
+  auto capture = [&]() {
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    s->graph_steps = 0;
+    if (ds->comm) return;
     cudaGraph_t graph = nullptr;
     const int64_t launches_before = g_launches.load();
     if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -593,8 +637,17 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
     }
     cudaGetLastError();
     g_launches.store(launches_before);  // captured launches were not executed
-  }
+  };
+  bool need_capture = (s->graph_exec == nullptr) && max_steps >= poll_every;
   while (n < max_steps) {
+    if (need_capture) {
+      // one eager step first: creates the plan / workspace of this batch size outside the capture
+      int rc = one_step();
+      if (rc) return rc;
+      ++n;
+      capture();
+      need_capture = false;
+    }
     if (s->graph_exec && max_steps - n >= s->graph_steps) {
       CU_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
       g_launches.fetch_add(2 * (int64_t)s->graph_steps);
@@ -609,6 +662,20 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
     CU_TRY(cudaMemcpyAsync(&done, p.n_done, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
     if (done >= p.C) break;
+    // compaction: evaluate only the chains that are still running (whole 128-chain steps)
+    if (s->compaction) {
+      const int active = p.C - done;
+      const int rows = std::min(p.C, (active + 127) / 128 * 128);
+      if (rows < s->n_rows) {
+        if (f32) nuts_compact_kernel<float><<<1, 1024, 0, s->stream>>>(p);
+        else nuts_compact_kernel<double><<<1, 1024, 0, s->stream>>>(p);
+        CU_TRY(cudaGetLastError());
+        g_launches.fetch_add(1);
+        s->n_rows = rows;
+        need_capture = max_steps - n >= poll_every;
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+      }
+    }
   }
   s->steps += n;
   if (steps_done) *steps_done = s->steps;
