@@ -179,7 +179,10 @@ __device__ __forceinline__ SoftSig softsig(float x) {
   r.inr = CLAMP ? (r.xc == x) : true;
   const float t = ex2(-fabsf(r.xc) * kLog2e);   // e^{-|x|} in (0,1]
   const float u = 1.0f + t;
-  const float inv = rcp(u);
+  float inv = rcp(u);
+  // one Newton step: MUFU.RCP's error is slightly biased and a bias adds up linearly over 10^7 visits
+  // (measured at config 2 near the mode: gradient error 9.0e-6 -> 4.2e-6 of |g|inf for +3 % time)
+  inv = fmaf(inv, fmaf(-u, inv, 1.0f), inv);
   r.s = fmaf(lg2(u), kLn2, fmaxf(r.xc, 0.0f));
   r.p = (r.xc >= 0.0f) ? inv : t * inv;
   return r;

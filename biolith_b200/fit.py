@@ -121,13 +121,46 @@ def fit(
         pass  # simulate() returns ell even without coords; meaningless without a spatial effect
     fpc = bool(kwargs.get("false_positives_constant", False))
     fpu = bool(kwargs.get("false_positives_unoccupied", False))
+    from .likelihood import ensure_period_dim
+
+    _, _, obs_np4, _ = ensure_period_dim(None, None, _as_numpy(obs), None)
+    n_sp = obs_np4.shape[0]
+    n_periods = obs_np4.shape[2]
+    if n_sp > 1 and (fpc or fpu):
+        raise BiolithB200Error(-2, "fit", "n_species > 1 with shared false-positive parameters couples the species "
+                               "and is outside the accelerated path")
+    parts = []
+    for sp in range(n_sp):
+        # species are independent problems sharing the covariates (one handle each, occu.py:182-186)
+        parts.append(_fit_one(name, site_covs, obs_covs, obs_np4[sp:sp + 1], session_duration, fpc, fpu, kwargs,
+                              dtype, device, num_chains, num_warmup, num_samples, random_seed + 7919 * sp,
+                              max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods))
+    grouped = {}
+    for k in parts[0][0]:
+        ax = 2 if k in ("beta", "alpha") else -1
+        if k in ("beta", "alpha", "psi", "abundance"):
+            grouped[k] = np.concatenate([p_[0][k] for p_ in parts], axis=ax)
+        else:
+            grouped[k] = parts[0][0][k]
+    extra = {k: (np.any([p_[1][k] for p_ in parts], axis=0) if k == "diverging"
+                 else np.mean([p_[1][k] for p_ in parts], axis=0) if k == "accept_prob"
+                 else np.sum([p_[1][k] for p_ in parts], axis=0))
+             for k in parts[0][1]}
+    info = parts[0][2] if n_sp == 1 else {"per_species": [p_[2] for p_ in parts]}
+    mcmc = MCMCResult(name, grouped, extra, num_samples, num_chains, info)
+    samples = mcmc.get_samples()
+    samples = rename_samples(samples, site_names, obs_names)
+    return FitResult(samples, mcmc)
+
+
+def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs, dtype, device, num_chains,
+             num_warmup, num_samples, seed, max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods):
+    """One species: pack, sample on the device, return (grouped samples, extra fields, info)."""
     lk = OccupancyLikelihood(
         name, site_covs, obs_covs, obs, session_duration, false_positives_constant=fpc,
         false_positives_unoccupied=fpu, max_abundance=kwargs.get("max_abundance", 100), dtype=dtype, prior=True,
         device=device, max_chains=num_chains, **prior_kw)
-    if n_species != 1 and _as_numpy(obs) is None:
-        raise BiolithB200Error(-2, "fit", "n_species > 1 needs one handle per species")
-    sampler = NutsSampler(lk, num_chains, num_warmup, num_samples, seed=random_seed,
+    sampler = NutsSampler(lk, num_chains, num_warmup, num_samples, seed=seed,
                           max_tree_depth=max_tree_depth, target_accept_prob=target_accept_prob)
     complete = sampler.run(timeout=timeout)
     if not complete:
@@ -160,17 +193,15 @@ def fit(
     if S * num_chains * num_samples <= _MAX_DETERMINISTIC_ELEMS:
         eta = th[:, :, 0:1] + np.einsum("cnk,sk->cns", th[:, :, 1 : Ks + 1], X)
         det = np.exp(eta) if name == "occu_rn" else 1 / (1 + np.exp(-eta))
-        grouped["abundance" if name == "occu_rn" else "psi"] = det[:, :, None, :, None]  # (C,N,P=1,S,Sp)
+        grouped["abundance" if name == "occu_rn" else "psi"] = np.broadcast_to(
+            det[:, :, None, :, None], det.shape[:2] + (n_periods, S, 1))  # (C,N,P,S,Sp)
     extra = dict(diverging=res["diverging"], accept_prob=res["accept_prob"], num_steps=res["num_steps"],
                  potential_energy=res["potential_energy"])
     info = dict(step_size=res["step_size"], inverse_mass_matrix=res["inverse_mass_matrix"],
                 leapfrogs=res["leapfrogs"], warmup_leapfrogs=res["warmup_leapfrogs"],
                 global_steps=res["global_steps"], wall_s=res["wall_s"], kernel_variant=lk.kernel_variant)
-    mcmc = MCMCResult(name, grouped, extra, num_samples, num_chains, info)
     lk.close()
-    samples = mcmc.get_samples()
-    samples = rename_samples(samples, site_names, obs_names)
-    return FitResult(samples, mcmc)
+    return grouped, extra, info
 
 
 def rename_samples(samples, site_covs_names=None, obs_covs_names=None):

@@ -89,3 +89,19 @@ def test_unsupported_options_raise():
         bb.fit(bb.models.occu, **data, site_random_effects=True)
     with pytest.raises(bb.BiolithB200Error):
         bb.fit(bb.models.occu, **data, kernel="hmc")
+
+
+def test_fit_multi_season_and_multi_species_like_reference_tests():
+    """biolith/models/occu.py:459-492: multi-period recovery (atol 0.15) and multi-species shapes."""
+    import biolith_b200 as bb
+
+    data, true = bb.simulate_occupancy("occu", simulate_missing=True, n_periods=3, random_seed=0)
+    res = bb.fit(bb.models.occu, **data, num_chains=4, num_samples=300, num_warmup=300, timeout=600)
+    assert res.samples["psi"].shape[1:] == (3, 100, 1)
+    assert np.allclose(res.samples["psi"].mean(), true["z"].mean(), atol=0.15)
+    data, _ = bb.simulate_occupancy("occu", simulate_missing=True, n_species=2, n_sites=30, random_seed=0)
+    res = bb.fit(bb.models.occu, **data, num_chains=2, num_samples=100, num_warmup=100, timeout=600)
+    assert res.samples["psi"].shape[-1] == 2
+    assert res.samples["cov_state_0"].shape == (200, 2)
+    with pytest.raises(bb.BiolithB200Error):
+        bb.fit(bb.models.occu, **data, false_positives_constant=True)
