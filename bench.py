@@ -373,9 +373,9 @@ def shard_is_chains(workload):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the eval kernel (ncu --set full), by workload
 PROFILED_TRAFFIC = {
-    # profiles/r01_occu_chain_v4.txt: 231.86 MB read + 7.63 MB written per launch (packed dataset: 128 MB;
+    # profiles/r01_occu_chain_v5.txt: 230.99 MB read + 10.07 MB written per launch (packed dataset: 128 MB;
     # the 4 chain chunks re-read tiles mostly from L2)
-    "occu_1m_x8_c1024": 239_495_168,
+    "occu_1m_x8_c1024": 241_061_376,
 }
 
 
