@@ -33,6 +33,9 @@ cudaError_t launch_occu(const EvalParams& p, int dtype, dim3 grid, size_t smem, 
 cudaError_t launch_occu_rn(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
 cudaError_t launch_occu_cop(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
 int occu_has_specialisation(int ks, int ko, bool fp);
+cudaError_t launch_occu_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
+cudaError_t launch_occu_rn_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
+cudaError_t launch_occu_cop_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
 int occu_derived_slots(uint32_t flags);
 int occu_rn_derived_slots(uint32_t flags);
 int occu_cop_derived_slots(uint32_t flags);
@@ -488,6 +491,46 @@ int bl_eval_host(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp
   memcpy(logp, ds->h_out, nl);
   memcpy(grad, (char*)ds->h_out + nl, nt);
   return BL_OK;
+}
+
+int bl_site_summary(bl_dataset* ds, const void* theta, int32_t n_draws, float* out) {
+  if (!ds || !theta || !out) return fail(BL_ERR_INVALID, "NULL argument");
+  if (n_draws < 1) return fail(BL_ERR_INVALID, "n_draws must be >= 1");
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  const size_t es = elem_size(ds->desc.dtype);
+  const size_t U = (size_t)ds->L.n_units;
+  if (U == 0) return BL_OK;
+  void* d_theta = nullptr;
+  float* d_out = nullptr;
+  void* d_scratch = nullptr;
+  int rc = BL_OK;
+  cudaError_t e = cudaSuccess;
+  do {
+#define CU_BRK(expr) if ((e = (expr)) != cudaSuccess) { rc = fail(BL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e)); break; }
+    CU_BRK(cudaMalloc(&d_theta, (size_t)n_draws * ds->D * es));
+    CU_BRK(cudaMalloc(&d_out, 4 * U * sizeof(float)));
+    CU_BRK(cudaMemcpy(d_theta, theta, (size_t)n_draws * ds->D * es, cudaMemcpyHostToDevice));
+    EvalParams p;
+    fill_params(ds, p);
+    p.theta = d_theta;
+    p.C = n_draws;
+    if (ds->desc.model == BL_MODEL_OCCU_RN) {
+      const size_t blocks = (U + kBlockThreads - 1) / kBlockThreads;
+      CU_BRK(cudaMalloc(&d_scratch, (size_t)(ds->desc.max_abundance + 1) * blocks * kBlockThreads * es));
+      p.rn_scratch_global = d_scratch;
+    }
+    switch (ds->desc.model) {
+      case BL_MODEL_OCCU: e = launch_occu_summary(p, ds->desc.dtype, d_out, nullptr); break;
+      case BL_MODEL_OCCU_RN: e = launch_occu_rn_summary(p, ds->desc.dtype, d_out, nullptr); break;
+      default: e = launch_occu_cop_summary(p, ds->desc.dtype, d_out, nullptr); break;
+    }
+    if (e != cudaSuccess) { rc = fail(BL_ERR_CUDA, "summary launch: %s", cudaGetErrorString(e)); break; }
+    g_launches.fetch_add(1);
+    CU_BRK(cudaMemcpy(out, d_out, 4 * U * sizeof(float), cudaMemcpyDeviceToHost));
+#undef CU_BRK
+  } while (0);
+  cudaFree(d_theta); cudaFree(d_out); cudaFree(d_scratch);
+  return rc;
 }
 
 int bl_eval_timed(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp, void* grad, bl_stream stream,

@@ -30,7 +30,8 @@ constexpr int kMaxStages = 4;
 //            [Ks, Ks + J*Ko)         W_{j,k} at Ks + j*Ko + k
 //            occu / occu_rn:  NW = ceil(J/32) words of y bits, NW words of mask bits, then n1 = number of
 //                             unmasked detections as a float (data-only; z=0 branch / k=0 state)
-//            occu_cop:        J floats y (0 if masked), J floats T (0 if masked), Sy, ST, NW mask words
+//            occu_cop:        J floats y (0 if masked), J floats T (0 if masked), Sy, ST, the per-unit
+//                             data constant sum m (y log T - lgamma(y+1)), NW mask words
 //   every warp-wide read of one field is one coalesced 128-byte (fp32) line, and a whole tile is a
 //   contiguous, 16-byte aligned chunk -> one cp.async.bulk (TMA) per block-tile.
 // ------------------------------------------------------------------------------------------
@@ -42,7 +43,7 @@ struct Layout {
   int off_y;       // y bits (occu/rn) or y floats (cop)
   int off_m;       // mask bit words
   int off_t;       // cop: T floats
-  int off_sy;      // cop: sum of masked y; +1 = sum of masked T
+  int off_sy;      // cop: sum of masked y; +1 = sum of masked T; +2 = sum m (y log T - lgamma(y+1))
   int off_n1;      // occu/rn: float count of unmasked detections
   int64_t n_units; // S*P
   int64_t n_tiles; // ceil(n_units/32)
@@ -58,7 +59,7 @@ inline Layout make_layout(int model, int64_t S, int P, int J, int ks, int ko) {
   if (model == BL_MODEL_OCCU_COP) {
     L.off_y = f; f += J;
     L.off_t = f; f += J;
-    L.off_sy = f; f += 2;
+    L.off_sy = f; f += 3;
     L.off_m = f; f += L.nw;
     L.off_n1 = -1;
   } else {

@@ -199,6 +199,75 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalPar
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-unit posterior summaries over a batch of draws (the deterministic
+// `psi` / `abundance` sites and the pointwise log-likelihood that the reference materialises per draw,
+// biolith/models/occu.py:207, utils/predict.py:67-72, evaluation/lppd.py, waic.py -- here streamed:
+// nothing of size draws x sites ever exists).  lane = unit, draws staged through shared memory.
+//   out[0][u] = mean_n psi_u(theta_n)            (occu_rn: mean lambda_u)
+//   out[1][u] = mean_n P(z_u = 1 | y, theta_n)   (occu_rn: mean E[N_u | y, theta_n])
+//   out[2][u] = log mean_n exp(l_u(theta_n))     (pointwise marginal lppd)
+//   out[3][u] = var_n l_u(theta_n)               (pointwise p_waic)
+// ------------------------------------------------------------------------------------------
+constexpr int kSummaryDraws = 32;  // draws staged per chunk
+
+template <typename T, class Model>
+__global__ void __launch_bounds__(kBlockThreads) summary_kernel(const EvalParams p, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* s_theta = reinterpret_cast<T*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int D = p.D, DS = p.DS, N = p.C;
+  const int64_t unit = (int64_t)blockIdx.x * kBlockThreads + tid;
+  const bool valid = unit < p.L.n_units;
+  const int64_t tile_idx = valid ? unit / kWarp : 0;
+  const T* tile = reinterpret_cast<const T*>(p.packed) + tile_idx * (int64_t)p.L.F * kWarp;
+  typename Model::Site site;
+  Model::load_site(p, tile, lane, site);
+  double s1 = 0.0, s2 = 0.0, mean = 0.0, m2 = 0.0, mx = -1e300, se = 0.0;
+  for (int c0 = 0; c0 < N; c0 += kSummaryDraws) {
+    const int nc = min(kSummaryDraws, N - c0);
+    __syncthreads();
+    for (int i = tid; i < nc * D; i += kBlockThreads)
+      s_theta[(i / D) * DS + (i % D)] = reinterpret_cast<const T*>(p.theta)[(size_t)c0 * D + i];
+    __syncthreads();
+    if constexpr (Model::kDerived > 0) {
+      for (int ci = tid; ci < nc; ci += kBlockThreads) Model::derive(p, s_theta + (size_t)ci * DS);
+      __syncthreads();
+    }
+    for (int ci = 0; ci < nc; ++ci) {
+      T q[Model::kNQMax];
+      T ex[2] = {T(0), T(0)};
+      Model::site_chain(p, tile, lane, site, s_theta + (size_t)ci * DS, q, ex);
+      const double ell = (double)q[0] + (double)Model::unit_const(p, tile, lane);
+      s1 += (double)ex[0];
+      s2 += (double)ex[1];
+      const double n = (double)(c0 + ci + 1);
+      const double d = ell - mean;
+      mean += d / n;
+      m2 += d * (ell - mean);
+      if (ell > mx) { se = se * exp(mx - ell) + 1.0; mx = ell; }
+      else se += exp(ell - mx);
+    }
+  }
+  if (valid) {
+    const int64_t U = p.L.n_units;
+    out[unit] = (float)(s1 / N);
+    out[U + unit] = (float)(s2 / N);
+    out[2 * U + unit] = (float)(mx + log(se / N));
+    out[3 * U + unit] = (float)(N > 1 ? m2 / (N - 1) : 0.0);
+  }
+}
+
+template <typename T, class Model>
+cudaError_t launch_summary(const EvalParams& p, float* out, cudaStream_t st) {
+  auto kern = summary_kernel<T, Model>;
+  const size_t smem = (size_t)kSummaryDraws * p.DS * sizeof(T) + 128;
+  const unsigned blocks = (unsigned)((p.L.n_units + kBlockThreads - 1) / kBlockThreads);
+  if (blocks == 0) return cudaSuccess;
+  kern<<<blocks, kBlockThreads, smem, st>>>(p, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launch geometry
 // ------------------------------------------------------------------------------------------
 struct Geometry {

@@ -32,6 +32,7 @@ struct OccuModel {
     T x[KSM];
     T n1, n0;  // masked detections / non-detections (data only)
   };
+  static __device__ __forceinline__ T unit_const(const EvalParams&, const T*, int) { return T(0); }
 
   static __device__ __forceinline__ void derive(const EvalParams& p, T* th) {
     if constexpr (FP) {
@@ -73,7 +74,8 @@ struct OccuModel {
   }
 
   static __device__ __forceinline__ void site_chain(const EvalParams& p, const T* __restrict__ tile, int lane,
-                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q) {
+                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q,
+                                                    T* __restrict__ extra = nullptr) {
     const int ks = kGeneric ? p.L.ks : KS;
     const int ko = kGeneric ? p.L.ko : KO;
     const int J = p.L.J;
@@ -163,9 +165,10 @@ struct OccuModel {
       L0 = N::fma_(s.n1, d[1], s.n0 * d[2]);
       dL0 = s.n1 * d[3] - s.n0 * d[4];  // dL0/dP0 (zero when P0 is clipped)
     }
-    T ell, r, geta;
+    T ell, r, geta, psi_out;
     if constexpr (kSfu) {
       const sfu::SoftSig se = sfu::softsig<true>(eta);
+      psi_out = se.p;
       const float av = (se.xc - se.s) + L1;
       const float bv = L0 - se.s;
       const float dd = av - bv;
@@ -177,6 +180,7 @@ struct OccuModel {
       geta = se.inr ? (r - se.p) : 0.f;
     } else {
       const LogSig<T> se = log_sigmoid_pair<T>(eta);
+      psi_out = se.p;
       const T av = se.lp + L1;
       const T bv = se.l1mp + L0;
       const T dd = av - bv;
@@ -186,6 +190,7 @@ struct OccuModel {
       ell = N::max_(av, bv) + N::log1p_(td);
       geta = se.inr ? (r - se.p) : T(0);
     }
+    if (extra) { extra[0] = psi_out; extra[1] = r; }
     q[0] = ell;
     q[1] = geta;
 #pragma unroll
@@ -242,6 +247,15 @@ cudaError_t launch_occu(const EvalParams& p, int dtype, dim3 grid, size_t smem, 
   if (dtype == BL_F64) return dispatch<double, true>(p, grid, smem, stream, occ);
   return (p.flags & BL_FLAG_STRICT_MATH) ? dispatch<float, true>(p, grid, smem, stream, occ)
                                          : dispatch<float, false>(p, grid, smem, stream, occ);
+}
+
+cudaError_t launch_occu_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st) {
+  const bool fp = (p.flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) != 0;
+  if (dtype == BL_F64)
+    return fp ? launch_summary<double, OccuModel<double, -1, -1, true, true>>(p, out, st)
+              : launch_summary<double, OccuModel<double, -1, -1, false, true>>(p, out, st);
+  return fp ? launch_summary<float, OccuModel<float, -1, -1, true, true>>(p, out, st)
+            : launch_summary<float, OccuModel<float, -1, -1, false, true>>(p, out, st);
 }
 
 int occu_derived_slots(uint32_t flags) {

@@ -30,6 +30,9 @@ struct OccuCopModel {
     T x[KSM];
     T sy, st;
   };
+  static __device__ __forceinline__ T unit_const(const EvalParams& p, const T* tile, int lane) {
+    return tile[(p.L.off_sy + 2) * kWarp + lane];
+  }
 
   static __device__ __forceinline__ void derive(const EvalParams& p, T* th) {
     T* d = th + p.D;
@@ -55,7 +58,8 @@ struct OccuCopModel {
   }
 
   static __device__ __forceinline__ void site_chain(const EvalParams& p, const T* __restrict__ tile, int lane,
-                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q) {
+                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q,
+                                                    T* __restrict__ extra = nullptr) {
     const int ks = kGeneric ? p.L.ks : KS;
     const int ko = kGeneric ? p.L.ko : KO;
     const int J = p.L.J;
@@ -126,6 +130,7 @@ struct OccuCopModel {
       ell = N::max_(av, bv) + (kSfu ? M::log_(T(1) + td) : N::log1p_(td));
     }
     const T geta = in_psi ? (r - psi) : T(0);
+    if (extra) { extra[0] = psi; extra[1] = r; }
     q[0] = ell;
     q[1] = geta;
 #pragma unroll
@@ -382,6 +387,11 @@ cudaError_t launch_occu_cop(const EvalParams& p, int dtype, dim3 grid, size_t sm
                : launch_cop_one<float, -1, -1, true>(p, grid, smem, stream, occ);
   return s53 ? launch_cop_one<float, 5, 3, false>(p, grid, smem, stream, occ)
              : launch_cop_one<float, -1, -1, false>(p, grid, smem, stream, occ);
+}
+
+cudaError_t launch_occu_cop_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st) {
+  if (dtype == BL_F64) return launch_summary<double, OccuCopModel<double, -1, -1, true>>(p, out, st);
+  return launch_summary<float, OccuCopModel<float, -1, -1, true>>(p, out, st);
 }
 
 int occu_cop_derived_slots(uint32_t) { return 6; }

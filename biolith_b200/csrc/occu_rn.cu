@@ -37,6 +37,7 @@ struct OccuRnModel {
   struct Site {
     T x[KSM];
   };
+  static __device__ __forceinline__ T unit_const(const EvalParams&, const T*, int) { return T(0); }
 
   static __device__ __forceinline__ void derive(const EvalParams& p, T* th) {
     T* d = th + p.D;
@@ -60,7 +61,8 @@ struct OccuRnModel {
   }
 
   static __device__ __forceinline__ void site_chain(const EvalParams& p, const T* __restrict__ tile, int lane,
-                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q) {
+                                                    const Site& s, const T* __restrict__ th, T* __restrict__ q,
+                                                    T* __restrict__ extra = nullptr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // per-thread column A[k] at scratch[k * 256 + tid] (placed after the engine's regions)
     // (or, when (K+1) x 256 elements do not fit, at global scratch[k * n_threads + gtid], coalesced)
@@ -160,6 +162,7 @@ struct OccuRnModel {
     }
     const T ell = (Mx + M::log_(Z)) - logZp;
     const T geta = Eq - Ep;
+    if (extra) { extra[0] = N::exp_(eta); extra[1] = Eq; }  // lambda, E[N | y]
 
     // ---- pass 2: dl/dnu_j = sum_k w_k dt_kj/dnu  (and dl/dc)
     T ga0 = T(0), gc = T(0);
@@ -583,6 +586,13 @@ cudaError_t launch_occu_rn(const EvalParams& p, int dtype, dim3 grid, size_t sme
                : launch_rn_one<float, -1, -1, true>(p, grid, smem, stream, occ);
   return s53 ? launch_rn_one<float, 5, 3, false>(p, grid, smem, stream, occ)
              : launch_rn_one<float, -1, -1, false>(p, grid, smem, stream, occ);
+}
+
+cudaError_t launch_occu_rn_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st) {
+  cudaError_t e = ensure_lgamma_table();
+  if (e != cudaSuccess) return e;
+  if (dtype == BL_F64) return launch_summary<double, OccuRnModel<double, -1, -1, true>>(p, out, st);
+  return launch_summary<float, OccuRnModel<float, -1, -1, true>>(p, out, st);
 }
 
 int occu_rn_derived_slots(uint32_t) { return 4; }

@@ -41,6 +41,7 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
   uint32_t yw = 0, mw = 0;
   int n1 = 0;
   TO sy = TO(0), st = TO(0);
+  double cst = 0.0;
   unsigned long long masked = 0;
   for (int j = 0; j < J; ++j) {
     bool cov_nan = site_nan;
@@ -58,7 +59,10 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
       if (m && (yv < TO(0) || !isfinite(tv))) atomicOr(err_flag, 2);
       base[(L.off_y + j) * kWarp] = m ? yv : TO(0);
       base[(L.off_t + j) * kWarp] = m ? tv : TO(0);
-      if (m) { sy += yv; st += tv; }
+      if (m) {
+        sy += yv; st += tv;
+        cst += (yv > TO(0) ? (double)yv * log((double)tv) : 0.0) - lgamma((double)yv + 1.0);
+      }
     } else {
       if (m) {
         if (yv == TO(1)) { yw |= 1u << (j & 31); ++n1; }
@@ -74,6 +78,7 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
   if (model == BL_MODEL_OCCU_COP) {
     base[L.off_sy * kWarp] = sy;
     base[(L.off_sy + 1) * kWarp] = st;
+    base[(L.off_sy + 2) * kWarp] = (TO)cst;
   } else {
     base[L.off_n1 * kWarp] = (TO)n1;
   }

@@ -200,6 +200,11 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs,
     info = dict(step_size=res["step_size"], inverse_mass_matrix=res["inverse_mass_matrix"],
                 leapfrogs=res["leapfrogs"], warmup_leapfrogs=res["warmup_leapfrogs"],
                 global_steps=res["global_steps"], wall_s=res["wall_s"], kernel_variant=lk.kernel_variant)
+    # per-site posterior summaries (psi / occupancy probability / pointwise lppd, p_waic), streamed on the
+    # GPU over <= 512 thinned draws: available at any n_sites, unlike the per-draw deterministic sites
+    flat = th.reshape(-1, th.shape[-1])
+    thin = flat[:: max(1, flat.shape[0] // 512)][:512]
+    info["site_summary"] = lk.site_summary(thin)
     lk.close()
     return grouped, extra, info
 

@@ -179,6 +179,31 @@ class OccupancyLikelihood:
                                       C.byref(ms)), "bl_eval_timed")
         return float(ms.value)
 
+    def site_summary(self, theta_draws) -> dict:
+        """Per-unit posterior summaries over a batch of draws, streamed on the GPU (no draws x sites
+        array is ever formed).  theta_draws: (N, D).  Arrays are (n_sites, n_periods).
+
+        ``psi_mean`` (occu_rn: ``abundance_mean``), ``occupancy_prob`` = mean P(z=1 | y) (occu_rn:
+        ``abundance_posterior_mean`` = mean E[N | y]), ``lppd`` and ``p_waic`` pointwise on the
+        marginalised unit, and their totals / ``waic`` on the deviance scale."""
+        th = np.ascontiguousarray(theta_draws, dtype=self.np_dtype)
+        if th.ndim != 2 or th.shape[1] != self.theta_dim:
+            raise ValueError(f"theta_draws must have shape (N, {self.theta_dim})")
+        s = self.shape
+        U = s["n_sites"] * s["n_periods"]
+        out = np.empty((4, U), dtype=np.float32)
+        check(self._lib.bl_site_summary(self._h, th.ctypes.data, th.shape[0], out.ctypes.data), "bl_site_summary")
+        out = out.reshape(4, s["n_sites"], s["n_periods"])
+        rn = self.model == "occu_rn"
+        lppd, p_waic = out[2].astype(np.float64), out[3].astype(np.float64)
+        return {
+            ("abundance_mean" if rn else "psi_mean"): out[0],
+            ("abundance_posterior_mean" if rn else "occupancy_prob"): out[1],
+            "lppd": out[2], "p_waic": out[3],
+            "lppd_total": float(lppd.sum()), "p_waic_total": float(p_waic.sum()),
+            "waic": float(-2.0 * (lppd.sum() - p_waic.sum())),
+        }
+
     def mask(self) -> np.ndarray:
         """(S, P, J) bool: which observations enter the likelihood (the bit-exact mask contract)."""
         s = self.shape

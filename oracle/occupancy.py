@@ -608,3 +608,23 @@ def expected_mask(site_covs, obs_covs, obs) -> np.ndarray:
     obs = np.asarray(obs)
     cov_nan = np.isnan(obs_covs).any(axis=-1) | np.isnan(site_covs).any(axis=-1)[:, None, None]
     return np.isfinite(obs) & ~cov_nan[None, ...]
+
+
+def site_summary(model: str, thetas, pr: Prepared, **kw):
+    """Per-unit posterior summaries over draws (checker for bl_site_summary): arrays of length S*P."""
+    fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad}[model]
+    ells, a1, a2 = [], [], []
+    for th in np.asarray(thetas, np.float64):
+        _, _, t = fn(th, pr, prior=False, return_site_terms=True, **kw)
+        ells.append(t["ell"])
+        if model == "occu_rn":
+            K = t["w"].shape[1] - 1
+            a1.append(np.exp(t["eta"]))
+            a2.append((t["w"] * np.arange(K + 1)).sum(axis=1))
+        else:
+            a1.append(t["psi"])
+            a2.append(t["r"])
+    ells = np.stack(ells)
+    n = ells.shape[0]
+    return dict(a1=np.mean(a1, axis=0), a2=np.mean(a2, axis=0), lppd=logsumexp(ells, axis=0) - np.log(n),
+                p_waic=ells.var(axis=0, ddof=1) if n > 1 else np.zeros(ells.shape[1]))

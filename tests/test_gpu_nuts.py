@@ -57,6 +57,12 @@ def test_fit_mirror_recovers_truth_like_reference_test():
     assert s["cov_state_0"].shape == (8 * 300, 1)
     summ = res.mcmc.summary()
     assert np.all(summ["beta"]["r_hat"] < 1.05)
+    ss = res.mcmc.info["site_summary"]
+    assert ss["psi_mean"].shape == (100, 1)
+    assert np.allclose(ss["psi_mean"].mean(), s["psi"].mean(), atol=5e-3)
+    # sites with a detection are occupied with certainty; the others less likely than a priori
+    det = np.nansum(data["obs"][0, :, 0, :], axis=1) > 0
+    assert np.all(ss["occupancy_prob"][det, 0] > 0.999) and np.all(ss["occupancy_prob"][~det, 0] < ss["psi_mean"][~det, 0])
 
 
 def test_fit_rn_and_cop_recover_truth():

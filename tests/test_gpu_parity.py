@@ -273,3 +273,31 @@ def test_cop_chain_kernel_against_oracle(ks, ko, fpc, fpu):
         assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"cop chain ks={ks} fpc={fpc} fpu={fpu}")
         lp_e, gr_e = lk.logp_and_grad(th[:8])  # site-parallel engine on the same handle
         np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("name", ["occu_missing", "occu_fp_const", "rn_5x3", "cop_missing_5x3", "cop_both_fp"])
+def test_site_summary_streaming_kernel(name, dtype):
+    """bl_site_summary (psi / occupancy probability / pointwise lppd and p_waic per unit, streamed over
+    draws) against the oracle's per-site terms."""
+    from oracle import occupancy as orc
+
+    g = load_golden(name)
+    d = g["data"]
+    rng = np.random.default_rng(1)
+    draws = g["thetas"][0] + 0.1 * rng.standard_normal((45, g["thetas"].shape[1]))
+    pr = orc.prepare(d["site_covs"], d["obs_covs"], d["obs"], d.get("session_duration"),
+                     dtype=np.float32 if dtype == "float32" else np.float64)
+    ref = orc.site_summary(g["model"], draws.astype(np.float32 if dtype == "float32" else np.float64), pr,
+                           dtype=np.float32 if dtype == "float32" else np.float64, **g["model_kwargs"])
+    with _make(g, dtype, prior=False) as lk:
+        out = lk.site_summary(draws)
+    rn = g["model"] == "occu_rn"
+    tol = 2e-5 if dtype == "float32" else 1e-6  # outputs are float32 either way
+    a1 = out["abundance_mean" if rn else "psi_mean"].ravel()
+    a2 = out["abundance_posterior_mean" if rn else "occupancy_prob"].ravel()
+    np.testing.assert_allclose(a1, ref["a1"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(a2, ref["a2"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(out["lppd"].ravel(), ref["lppd"], rtol=tol, atol=20 * tol)
+    np.testing.assert_allclose(out["p_waic"].ravel(), ref["p_waic"], rtol=2e-3, atol=1e-5)
+    assert abs(out["lppd_total"] - ref["lppd"].sum()) <= 1e-5 * abs(ref["lppd"].sum())
