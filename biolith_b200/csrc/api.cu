@@ -26,12 +26,14 @@ int fail(int code, const char* fmt, ...) {
 
 // kernels defined in the per-model translation units
 cudaError_t launch_pack(int data_dtype, int dtype, const void* y, const void* X, const void* W, const void* T,
-                        void* out, const Layout& L, int model, int* err_flag, unsigned long long* n_masked,
+                        void* out, const Layout& L, int model, int K, int* err_flag, unsigned long long* n_masked,
                         cudaStream_t st);
 cudaError_t launch_export_mask(int dtype, const void* packed, uint8_t* mask, const Layout& L, cudaStream_t st);
 cudaError_t launch_occu(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
 cudaError_t launch_occu_rn(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
 cudaError_t launch_occu_cop(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
+cudaError_t launch_nmixture(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
+cudaError_t launch_nmixture_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
 int occu_has_specialisation(int ks, int ko, bool fp);
 cudaError_t launch_occu_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
 cudaError_t launch_occu_rn_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
@@ -63,6 +65,7 @@ static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 
   switch (ds->desc.model) {
     case BL_MODEL_OCCU: return launch_occu(p, ds->desc.dtype, grid, smem, st, occ);
     case BL_MODEL_OCCU_RN: return launch_occu_rn(p, ds->desc.dtype, grid, smem, st, occ);
+    case BL_MODEL_NMIXTURE: return launch_nmixture(p, ds->desc.dtype, grid, smem, st, occ);
     default: return launch_occu_cop(p, ds->desc.dtype, grid, smem, st, occ);
   }
 }
@@ -96,7 +99,8 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     Plan pl{};
     const int elem = (int)elem_size(ds->desc.dtype);
     size_t extra = 0;
-    if (ds->desc.model == BL_MODEL_OCCU_RN) extra = occu_rn_extra_smem(ds->L, ds->desc.max_abundance, elem);
+    if (ds->desc.model == BL_MODEL_OCCU_RN || ds->desc.model == BL_MODEL_NMIXTURE)
+      extra = occu_rn_extra_smem(ds->L, ds->desc.max_abundance, elem);  // per-thread (K+1) column
     pl.rn_global = false;
     if (extra && extra + 4096 < ds->smem_limit) {
       // the per-thread A_k column goes to shared memory when it fits beside the tile ring ...
@@ -277,7 +281,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   if (!d || !out) return fail(BL_ERR_INVALID, "desc/out is NULL");
   *out = nullptr;
   if (d->abi_version != BL_ABI_VERSION) return fail(BL_ERR_INVALID, "ABI version %d != %d", d->abi_version, BL_ABI_VERSION);
-  if (d->model < 0 || d->model > 2) return fail(BL_ERR_INVALID, "unknown model %d", d->model);
+  if (d->model < 0 || d->model > 3) return fail(BL_ERR_INVALID, "unknown model %d", d->model);
   if ((d->dtype != BL_F32 && d->dtype != BL_F64) || (d->data_dtype != BL_F32 && d->data_dtype != BL_F64))
     return fail(BL_ERR_INVALID, "dtype must be BL_F32 or BL_F64");
   if (d->n_sites < 0 || d->n_periods < 1 || d->n_replicates < 1 || d->n_site_covs < 0 || d->n_obs_covs < 0)
@@ -290,7 +294,8 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   if (d->model == BL_MODEL_OCCU && fpc && fpu)
     return fail(BL_ERR_INVALID, "false_positives_constant and false_positives_unoccupied cannot both be True");  // occu.py:112-114
   if (d->model == BL_MODEL_OCCU_RN && fpu) return fail(BL_ERR_INVALID, "occu_rn has no false_positives_unoccupied");
-  if (d->model == BL_MODEL_OCCU_RN && (d->max_abundance < 1 || d->max_abundance > 1023))
+  if (d->model == BL_MODEL_NMIXTURE && (fpc || fpu)) return fail(BL_ERR_INVALID, "nmixture has no false-positive options");
+  if ((d->model == BL_MODEL_OCCU_RN || d->model == BL_MODEL_NMIXTURE) && (d->max_abundance < 1 || d->max_abundance > 1023))
     return fail(BL_ERR_INVALID, "max_abundance must be in [1, 1023]");
   if (d->n_sites > 0 && (!y || !X || !W)) return fail(BL_ERR_INVALID, "y/X/W is NULL");
   if ((d->flags & BL_FLAG_PRIOR) && (d->prior_beta_scale <= 0 || d->prior_alpha_scale <= 0))
@@ -305,7 +310,8 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   ds->n_extras = (fpc ? 1 : 0) + (fpu ? 1 : 0);
   ds->D = d->n_site_covs + 1 + d->n_obs_covs + 1 + ds->n_extras;
   int derived = d->model == BL_MODEL_OCCU ? occu_derived_slots(d->flags)
-                : d->model == BL_MODEL_OCCU_RN ? occu_rn_derived_slots(d->flags) : occu_cop_derived_slots(d->flags);
+                : d->model == BL_MODEL_OCCU_RN ? occu_rn_derived_slots(d->flags)
+                : d->model == BL_MODEL_OCCU_COP ? occu_cop_derived_slots(d->flags) : 0;
   ds->DS = ds->D + derived;
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
@@ -342,7 +348,8 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
         CU_BRK(cudaMalloc(&dT, nobs * ds_in));
         CU_BRK(cudaMemcpy(dT, T, nobs * ds_in, cudaMemcpyDefault));
       }
-      CU_BRK(launch_pack(d->data_dtype, d->dtype, dy, dX, dW, dT, ds->packed, L, d->model, d_err, d_nm, nullptr));
+      CU_BRK(launch_pack(d->data_dtype, d->dtype, dy, dX, dW, dT, ds->packed, L, d->model, d->max_abundance, d_err,
+                         d_nm, nullptr));
       g_launches.fetch_add(1);
       CU_BRK(cudaDeviceSynchronize());
     }
@@ -353,6 +360,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
     ds->n_masked = (int64_t)h_nm;
     if (h_err & 1) { rc = fail(BL_ERR_BAD_DATA, "detections must be binary (0/1) or non-finite (missing)"); break; }
     if (h_err & 2) { rc = fail(BL_ERR_BAD_DATA, "counts must be >= 0 and session_duration finite"); break; }
+    if (h_err & 4) { rc = fail(BL_ERR_BAD_DATA, "nmixture counts must be integers in [0, max_abundance]"); break; }
 #undef CU_BRK
   } while (0);
   cudaFree(dy); cudaFree(dX); cudaFree(dW); cudaFree(dT); cudaFree(d_err); cudaFree(d_nm);
@@ -514,7 +522,7 @@ int bl_site_summary(bl_dataset* ds, const void* theta, int32_t n_draws, float* o
     fill_params(ds, p);
     p.theta = d_theta;
     p.C = n_draws;
-    if (ds->desc.model == BL_MODEL_OCCU_RN) {
+    if (ds->desc.model == BL_MODEL_OCCU_RN || ds->desc.model == BL_MODEL_NMIXTURE) {
       const size_t blocks = (U + kBlockThreads - 1) / kBlockThreads;
       CU_BRK(cudaMalloc(&d_scratch, (size_t)(ds->desc.max_abundance + 1) * blocks * kBlockThreads * es));
       p.rn_scratch_global = d_scratch;
@@ -522,6 +530,7 @@ int bl_site_summary(bl_dataset* ds, const void* theta, int32_t n_draws, float* o
     switch (ds->desc.model) {
       case BL_MODEL_OCCU: e = launch_occu_summary(p, ds->desc.dtype, d_out, nullptr); break;
       case BL_MODEL_OCCU_RN: e = launch_occu_rn_summary(p, ds->desc.dtype, d_out, nullptr); break;
+      case BL_MODEL_NMIXTURE: e = launch_nmixture_summary(p, ds->desc.dtype, d_out, nullptr); break;
       default: e = launch_occu_cop_summary(p, ds->desc.dtype, d_out, nullptr); break;
     }
     if (e != cudaSuccess) { rc = fail(BL_ERR_CUDA, "summary launch: %s", cudaGetErrorString(e)); break; }

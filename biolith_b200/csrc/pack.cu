@@ -25,7 +25,7 @@ template <> __device__ __forceinline__ double word_as<double>(uint32_t w) {
 
 template <typename TI, typename TO>
 __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, const TI* __restrict__ W,
-                            const TI* __restrict__ Tdur, TO* __restrict__ out, Layout L, int model,
+                            const TI* __restrict__ Tdur, TO* __restrict__ out, Layout L, int model, int K,
                             int* __restrict__ err_flag, unsigned long long* __restrict__ n_masked) {
   const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= L.n_units) return;
@@ -38,10 +38,12 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
     site_nan |= isnan(v);
     base[k * kWarp] = nan_to_num<TO>(v);
   }
-  uint32_t yw = 0, mw = 0;
+  uint32_t ybits = 0, mw = 0;
   int n1 = 0;
   TO sy = TO(0), st = TO(0);
   double cst = 0.0;
+  TO ymax = TO(0), y0 = TO(0), yw[kMaxCov];
+  for (int k = 0; k < kMaxCov; ++k) yw[k] = TO(0);
   unsigned long long masked = 0;
   for (int j = 0; j < J; ++j) {
     bool cov_nan = site_nan;
@@ -54,7 +56,15 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
     const bool m = isfinite(yv) && !cov_nan;
     masked += m ? 0 : 1;
     if (m) mw |= 1u << (j & 31);
-    if (model == BL_MODEL_OCCU_COP) {
+    if (model == BL_MODEL_NMIXTURE) {
+      if (m && (yv < TO(0) || yv != floor(yv) || yv > (TO)K)) atomicOr(err_flag, 4);
+      base[(L.off_y + j) * kWarp] = m ? yv : TO(0);
+      if (m) {
+        ymax = yv > ymax ? yv : ymax;
+        y0 += yv;
+        for (int k = 0; k < ko; ++k) yw[k] += yv * base[(L.off_w + j * ko + k) * kWarp];
+      }
+    } else if (model == BL_MODEL_OCCU_COP) {
       const TO tv = Tdur ? (TO)Tdur[u * J + j] : TO(1);
       if (m && (yv < TO(0) || !isfinite(tv))) atomicOr(err_flag, 2);
       base[(L.off_y + j) * kWarp] = m ? yv : TO(0);
@@ -65,17 +75,22 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
       }
     } else {
       if (m) {
-        if (yv == TO(1)) { yw |= 1u << (j & 31); ++n1; }
+        if (yv == TO(1)) { ybits |= 1u << (j & 31); ++n1; }
         else if (yv != TO(0)) atomicOr(err_flag, 1);  // detections must be binary
       }
     }
     if ((j & 31) == 31 || j == J - 1) {
       base[(L.off_m + (j >> 5)) * kWarp] = word_as<TO>(mw);
-      if (model != BL_MODEL_OCCU_COP) base[(L.off_y + (j >> 5)) * kWarp] = word_as<TO>(yw);
-      yw = 0; mw = 0;
+      if (model != BL_MODEL_OCCU_COP && model != BL_MODEL_NMIXTURE)
+        base[(L.off_y + (j >> 5)) * kWarp] = word_as<TO>(ybits);
+      ybits = 0; mw = 0;
     }
   }
-  if (model == BL_MODEL_OCCU_COP) {
+  if (model == BL_MODEL_NMIXTURE) {
+    base[L.off_sy * kWarp] = ymax;
+    base[(L.off_sy + 1) * kWarp] = y0;
+    for (int k = 0; k < ko; ++k) base[(L.off_sy + 2 + k) * kWarp] = yw[k];
+  } else if (model == BL_MODEL_OCCU_COP) {
     base[L.off_sy * kWarp] = sy;
     base[(L.off_sy + 1) * kWarp] = st;
     base[(L.off_sy + 2) * kWarp] = (TO)cst;
@@ -97,14 +112,14 @@ __global__ void export_mask_kernel(const TO* __restrict__ packed, uint8_t* __res
 }
 
 cudaError_t launch_pack(int data_dtype, int dtype, const void* y, const void* X, const void* W, const void* T,
-                        void* out, const Layout& L, int model, int* err_flag, unsigned long long* n_masked,
+                        void* out, const Layout& L, int model, int K, int* err_flag, unsigned long long* n_masked,
                         cudaStream_t st) {
   const int threads = 256;
   const unsigned blocks = (unsigned)((L.n_units + threads - 1) / threads);
   if (blocks == 0) return cudaSuccess;
 #define BL_PACK(TI, TO)                                                                                        \
   pack_kernel<TI, TO><<<blocks, threads, 0, st>>>((const TI*)y, (const TI*)X, (const TI*)W, (const TI*)T,       \
-                                                  (TO*)out, L, model, err_flag, n_masked)
+                                                  (TO*)out, L, model, K, err_flag, n_masked)
   if (data_dtype == BL_F32 && dtype == BL_F32) BL_PACK(float, float);
   else if (data_dtype == BL_F64 && dtype == BL_F32) BL_PACK(double, float);
   else if (data_dtype == BL_F32 && dtype == BL_F64) BL_PACK(float, double);

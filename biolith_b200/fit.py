@@ -192,8 +192,8 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs,
     S = X.shape[0]
     if S * num_chains * num_samples <= _MAX_DETERMINISTIC_ELEMS:
         eta = th[:, :, 0:1] + np.einsum("cnk,sk->cns", th[:, :, 1 : Ks + 1], X)
-        det = np.exp(eta) if name == "occu_rn" else 1 / (1 + np.exp(-eta))
-        grouped["abundance" if name == "occu_rn" else "psi"] = np.broadcast_to(
+        det = np.exp(eta) if name in ("occu_rn", "nmixture") else 1 / (1 + np.exp(-eta))
+        grouped["abundance" if name in ("occu_rn", "nmixture") else "psi"] = np.broadcast_to(
             det[:, :, None, :, None], det.shape[:2] + (n_periods, S, 1))  # (C,N,P,S,Sp)
     extra = dict(diverging=res["diverging"], accept_prob=res["accept_prob"], num_steps=res["num_steps"],
                  potential_energy=res["potential_energy"])

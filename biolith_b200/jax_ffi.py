@@ -155,3 +155,4 @@ def _handle_cache(model_name, site_covs, obs_covs, obs, session_duration, fpc, f
 occu = _drop_in("occu")
 occu_rn = _drop_in("occu_rn")
 occu_cop = _drop_in("occu_cop")
+nmixture = _drop_in("nmixture")

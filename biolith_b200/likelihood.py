@@ -194,7 +194,7 @@ class OccupancyLikelihood:
         out = np.empty((4, U), dtype=np.float32)
         check(self._lib.bl_site_summary(self._h, th.ctypes.data, th.shape[0], out.ctypes.data), "bl_site_summary")
         out = out.reshape(4, s["n_sites"], s["n_periods"])
-        rn = self.model == "occu_rn"
+        rn = self.model in ("occu_rn", "nmixture")
         lppd, p_waic = out[2].astype(np.float64), out[3].astype(np.float64)
         return {
             ("abundance_mean" if rn else "psi_mean"): out[0],

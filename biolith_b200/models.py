@@ -28,7 +28,9 @@ occu = _Model("occu", "Bernoulli occupancy model (MacKenzie et al. 2002); biolit
 occu_rn = _Model("occu_rn", "Royle-Nichols abundance-induced heterogeneity; biolith/models/occu_rn.py:20-222")
 occu_cop = _Model("occu_cop", "Count-detection occupancy (Pautrel et al. 2024); biolith/models/occu_cop.py:18-255")
 
-SUPPORTED = {"occu": occu, "occu_rn": occu_rn, "occu_cop": occu_cop}
+nmixture = _Model("nmixture", "N-mixture model for repeated counts (Royle 2004); biolith/models/nmixture.py:19-220")
+
+SUPPORTED = {"occu": occu, "occu_rn": occu_rn, "occu_cop": occu_cop, "nmixture": nmixture}
 
 # keyword arguments of the reference models that the accelerated path honours / must reject
 HONOURED = {"false_positives_constant", "false_positives_unoccupied", "max_abundance", "n_species"}

@@ -33,6 +33,7 @@ Reference lines restated (paths relative to /root/reference):
   biolith/models/occu.py:135-242      (occu body)
   biolith/models/occu_rn.py:123-222   (occu_rn body)
   biolith/models/occu_cop.py:146-255  (occu_cop body)
+  biolith/models/nmixture.py:124-220  (nmixture body)
   biolith/regression/linear.py:16-66  (LinearRegression)
   biolith/utils/modeling.py:8-39      (mask_missing_obs / flatten / reshape)
   biolith/utils/distributions.py:6-40 (RightTruncatedPoisson)
@@ -43,6 +44,7 @@ numpyro>=0.18; recalled, not vendored):
   clamp_probs(p)            = clip(p, finfo.tiny, 1 - finfo.eps)
   BernoulliProbs.log_prob   = xlogy(v, p~) + xlog1py(1 - v, -p~)
   Poisson.log_prob          = xlogy(v, rate) - gammaln(v + 1) - rate
+  BinomialProbs.log_prob    = gammaln(n+1) - gammaln(v+1) - gammaln(n-v+1) + xlogy(v, p) + xlog1py(n-v, -p)
   CategoricalLogits         = logits - logsumexp(logits)   (normalised)
   MaskedDistribution        = where(m, base.log_prob(where(m, v, feasible)), 0)
   Beta / Exponential priors are sampled in unconstrained space through
@@ -335,6 +337,50 @@ def occu_cop_log_joint_enumerated(
     return float(lp + logsumexp(site_ll, axis=0).sum())
 
 
+
+def nmixture_log_joint_enumerated(theta, site_covs, obs_covs, obs, *, max_abundance=100, dtype=np.float32,
+                                  prior=True):
+    """nmixture.py:124-220 op by op (Royle 2004 N-mixture; truncated, un-renormalised Poisson prior)."""
+    pr = prepare(site_covs, obs_covs, obs, dtype=dtype)
+    Sp, S, P, J = pr.y.shape
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    theta = np.asarray(theta, np.float64)
+    nb, na = Sp * (Ks + 1), Sp * (Ko + 1)
+    beta = theta[:nb].reshape(Sp, Ks + 1)
+    alpha = theta[nb : nb + na].reshape(Sp, Ko + 1)
+    assert theta.size == nb + na
+    lp = 0.0
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+    site_flat, site_shape = _flatten(pr.X.transpose(1, 0))
+    obs_flat, obs_shape = _flatten(pr.W.transpose(3, 2, 1, 0))
+    y = pr.y.transpose(3, 2, 1, 0)  # (J,P,S,Sp)
+    m = np.isfinite(y)
+    # nmixture.py:167-171
+    obs_max = np.max(np.where(np.isnan(y), -np.inf, y), axis=0)
+    obs_max = np.where(np.isfinite(obs_max), obs_max, 0)
+    min_counts = obs_max.astype(int)  # (P,S,Sp)
+    abundance = np.broadcast_to(np.exp(_linear(beta, site_flat).reshape(site_shape + (Sp,))), (P, S, Sp))
+    support = np.arange(max_abundance + 1)
+    logits = poisson_log_prob(abundance[..., None], support.astype(np.float64))  # (P,S,Sp,K+1)
+    logits = np.where(support < min_counts[..., None], -np.inf, logits)
+    factor = logsumexp(logits, axis=-1)  # numpyro.factor("N_i_trunc_norm", ...), nmixture.py:187
+    with np.errstate(invalid="ignore"):
+        log_pN = logits - factor[..., None]  # Categorical(logits) normalises
+    log_pN = np.moveaxis(log_pN, -1, 0)[:, None]  # (K+1,1,P,S,Sp)
+    N = support.reshape(-1, 1, 1, 1, 1).astype(np.float64)
+    p = expit(_linear(alpha, obs_flat).reshape(obs_shape + (Sp,)))  # (J,P,S,Sp)
+    v = np.where(m, y, 0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ll = (gammaln(N + 1) - gammaln(v + 1) - gammaln(N - v + 1) + xlogy(v, p) + xlog1py(N - v, -p))
+        ll = np.where(N - v < 0, -np.inf, ll)  # gammaln(non-positive integer) = +inf
+    ll = np.where(m, ll, 0.0)
+    with np.errstate(invalid="ignore"):
+        site_ll = ll.sum(axis=1, keepdims=True) + log_pN
+    site_ll = np.where(np.isnan(site_ll), -np.inf, site_ll)
+    return float(lp + logsumexp(site_ll, axis=0).sum() + factor.sum())
+
+
 # ==================================================================== closed form
 def _softplus(x):
     return np.logaddexp(0.0, x)
@@ -568,10 +614,54 @@ def occu_cop_logp_grad(
     return logp, grad
 
 
+
+def nmixture_logp_grad(theta, pr: Prepared, *, max_abundance=100, dtype=np.float32, prior=True,
+                       return_site_terms=False):
+    """Closed-form N-mixture log-density + gradient.  Per unit, with u_j = log(1-p_j):
+       A_k = k (eta + sum_j m_j u_j) - lambda - lgamma(k+1) + sum_j m_j log C(k, y_j),  k >= max_j y_j
+       l   = sum_j m_j y_j nu_j + logsumexp_k A_k;   dl/deta = E_w[k] - lambda;  dl/dnu_j = m_j (y_j - p_j E_w[k])."""
+    X, W, T, y, m = _units(pr)
+    Ks, Ko = X.shape[1], W.shape[2]
+    beta, alpha, _, _ = split_theta(theta, Ks, Ko, False, False)
+    K = int(max_abundance)
+    k = np.arange(K + 1, dtype=np.float64)
+    eta = beta[0] + X @ beta[1:]
+    lam = np.exp(eta)
+    nu = alpha[0] + W @ alpha[1:]
+    p = expit(nu)
+    l1p = -_softplus(nu)
+    U = (m * l1p).sum(axis=1)
+    V = (m * y * nu).sum(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        lgc = gammaln(k[None, None, :] + 1) - gammaln(y[:, :, None] + 1) - gammaln(k[None, None, :] - y[:, :, None] + 1)
+        lgc = np.where(k[None, None, :] < y[:, :, None], -np.inf, lgc)
+    cst = np.where(m[:, :, None], lgc, 0.0).sum(axis=1)  # (U,K+1) data-only
+    A = k[None, :] * (eta + U)[:, None] - lam[:, None] - gammaln(k + 1.0)[None, :] + cst
+    ls = logsumexp(A, axis=1)
+    w = np.exp(A - ls[:, None])
+    Ek = (w * k).sum(axis=1)
+    ell = V + ls
+    d_eta = Ek - lam
+    d_nu = m * (y - p * Ek[:, None])
+    g_beta = np.concatenate([[d_eta.sum()], X.T @ d_eta])
+    g_alpha = np.concatenate([[d_nu.sum()], np.einsum("uj,ujk->k", d_nu, W)])
+    lp = 0.0
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+        g_beta = g_beta - beta
+        g_alpha = g_alpha - alpha
+    logp = float(lp + ell.sum())
+    grad = np.concatenate([g_beta, g_alpha]).astype(np.float64)
+    if return_site_terms:
+        return logp, grad, dict(ell=ell, w=w, eta=eta, nu=nu)
+    return logp, grad
+
+
 # ------------------------------------------------------------------ conveniences
 def logp_grad(model: str, theta, pr: Prepared, **kw):
     """Dispatch on model name; theta (D,) or (C, D) -> (logp[C], grad[C,D])."""
-    fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad}[model]
+    fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad,
+          "nmixture": nmixture_logp_grad}[model]
     theta = np.asarray(theta, np.float64)
     if theta.ndim == 1:
         return fn(theta, pr, **kw)
@@ -584,6 +674,7 @@ def log_joint_enumerated(model: str, theta, data: dict, **kw):
         "occu": occu_log_joint_enumerated,
         "occu_rn": occu_rn_log_joint_enumerated,
         "occu_cop": occu_cop_log_joint_enumerated,
+        "nmixture": nmixture_log_joint_enumerated,
     }[model]
     args = [data["site_covs"], data["obs_covs"], data["obs"]]
     if model == "occu_cop":
@@ -612,12 +703,13 @@ def expected_mask(site_covs, obs_covs, obs) -> np.ndarray:
 
 def site_summary(model: str, thetas, pr: Prepared, **kw):
     """Per-unit posterior summaries over draws (checker for bl_site_summary): arrays of length S*P."""
-    fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad}[model]
+    fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad,
+          "nmixture": nmixture_logp_grad}[model]
     ells, a1, a2 = [], [], []
     for th in np.asarray(thetas, np.float64):
         _, _, t = fn(th, pr, prior=False, return_site_terms=True, **kw)
         ells.append(t["ell"])
-        if model == "occu_rn":
+        if model in ("occu_rn", "nmixture"):
             K = t["w"].shape[1] - 1
             a1.append(np.exp(t["eta"]))
             a2.append((t["w"] * np.arange(K + 1)).sum(axis=1))

@@ -105,6 +105,10 @@ def main():
         ("cop_missing_5x3", "occu_cop", m.simulate_cop,
          dict(n_site_covs=5, n_obs_covs=3, n_sites=150, deployment_days_per_site=84, simulate_missing=True),
          dict(fp_constant=True)),
+        ("nmix_default", "nmixture", m.simulate_nmixture, dict(), dict(max_abundance=100)),
+        ("nmix_missing_5x3", "nmixture", m.simulate_nmixture,
+         dict(n_site_covs=5, n_obs_covs=3, n_sites=150, deployment_days_per_site=70, simulate_missing=True),
+         dict(max_abundance=60)),
         ("cop_both_fp", "occu_cop", m.simulate_cop,
          dict(n_site_covs=1, n_obs_covs=2, n_sites=80, deployment_days_per_site=70),
          dict(fp_constant=True, fp_unoccupied=True)),

@@ -111,3 +111,24 @@ def test_fit_multi_season_and_multi_species_like_reference_tests():
     assert res.samples["cov_state_0"].shape == (200, 2)
     with pytest.raises(bb.BiolithB200Error):
         bb.fit(bb.models.occu, **data, false_positives_constant=True)
+
+
+def test_fit_nmixture_recovers_truth():
+    """The reference's own acceptance test, biolith/models/nmixture.py:377-420 (same simulator settings,
+    max_abundance = largest observed count, abundance rtol 0.2, coefficients atol 0.5)."""
+    import biolith_b200 as bb
+
+    data, true = bb.simulate_occupancy("nmixture", simulate_missing=True, deployment_days_per_site=70,
+                                       session_duration=7, min_abundance=1.0, min_observation_rate=1.0,
+                                       max_observation_rate=6.0, random_seed=0)
+    K = int(np.nanmax(data["obs"]))
+    res = bb.fit(bb.models.nmixture, **data, max_abundance=K, num_chains=8, num_samples=300, num_warmup=300,
+                 timeout=600)
+    assert np.allclose(res.samples["abundance"].mean(), true["abundance"].mean(), rtol=0.2)
+    for i in range(2):
+        assert np.allclose(res.samples[f"cov_state_{i}"].mean(), true["beta"][0, i], atol=0.5)
+        assert np.allclose(res.samples[f"cov_det_{i}"].mean(), true["alpha"][0, i], atol=0.5)
+    ss = res.mcmc.info["site_summary"]
+    N_true = true["N"][0, 0, :]
+    assert np.corrcoef(ss["abundance_posterior_mean"][:, 0], N_true)[0, 1] > 0.8
+    assert np.all(res.mcmc.summary()["beta"]["r_hat"] < 1.05)

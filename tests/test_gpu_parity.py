@@ -11,7 +11,7 @@ from conftest import GOLDEN_NAMES, load_golden
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = {"occu", "occu_rn", "occu_cop"}
+IMPLEMENTED = {"occu", "occu_rn", "occu_cop", "nmixture"}
 RTOL = {"float32": 1e-5, "float64": 1e-10}
 
 
@@ -80,7 +80,7 @@ def test_chain_batching_is_consistent(n_chains):
 
 @pytest.mark.parametrize("S,P,J,ks,ko", [(1, 1, 1, 1, 1), (33, 1, 5, 2, 1), (257, 1, 8, 5, 3), (40, 3, 4, 3, 2),
                                          (1000, 1, 40, 1, 1), (64, 2, 33, 7, 9), (50, 1, 6, 0, 0)])
-@pytest.mark.parametrize("model", ["occu", "occu_rn", "occu_cop"])
+@pytest.mark.parametrize("model", ["occu", "occu_rn", "occu_cop", "nmixture"])
 def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
     import biolith_b200 as bb
     from oracle import occupancy as orc
@@ -92,6 +92,8 @@ def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
     W = rng.normal(size=(S, P, J, ko))
     if model == "occu_cop":
         y = rng.poisson(2.0, size=(1, S, P, J)).astype(float)
+    elif model == "nmixture":
+        y = rng.binomial(rng.poisson(3.0, size=(1, S, P, 1)), 0.4, size=(1, S, P, J)).astype(float)
     else:
         y = (rng.uniform(size=(1, S, P, J)) < 0.35).astype(float)
     # ragged visits: trailing replicates missing, plus NaNs in covariates
@@ -102,7 +104,8 @@ def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
     if ks and S > 3:
         X[rng.integers(0, S), rng.integers(0, ks)] = np.nan
     T = rng.uniform(0.5, 9.0, size=(S, P, J)) if model == "occu_cop" else None
-    kw = dict(fp_constant=True) if model == "occu_cop" else (dict(max_abundance=30) if model == "occu_rn" else {})
+    kw = dict(fp_constant=True) if model == "occu_cop" else (
+        dict(max_abundance=30) if model in ("occu_rn", "nmixture") else {})
     D = ks + ko + 2 + (1 if model == "occu_cop" else 0)
     th = rng.uniform(-1.5, 1.5, size=(6, D))
     pr = orc.prepare(X, W, y, T)
@@ -203,7 +206,8 @@ def test_config2_full_size_against_c_oracle():
         np.testing.assert_allclose(np.concatenate([gr_a, gr_b]), gr, rtol=1e-5, atol=1e-5 * np.abs(gr).max())
 
 
-@pytest.mark.parametrize("name", ["occu_5x3", "occu_missing", "rn_5x3", "cop_missing_5x3"])
+@pytest.mark.parametrize("name", ["occu_5x3", "occu_missing", "rn_5x3", "cop_missing_5x3", "nmix_missing_5x3",
+                                  "nmix_default"])
 def test_strict_math_flag(name):
     """BL_FLAG_STRICT_MATH (libm expf/log1pf/IEEE division) and the default bounded-error SFU forms
     both meet the fp32 tolerance; their mutual difference is at fp32-rounding level."""
@@ -276,7 +280,8 @@ def test_cop_chain_kernel_against_oracle(ks, ko, fpc, fpu):
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
-@pytest.mark.parametrize("name", ["occu_missing", "occu_fp_const", "rn_5x3", "cop_missing_5x3", "cop_both_fp"])
+@pytest.mark.parametrize("name", ["occu_missing", "occu_fp_const", "rn_5x3", "cop_missing_5x3", "cop_both_fp",
+                                  "nmix_missing_5x3"])
 def test_site_summary_streaming_kernel(name, dtype):
     """bl_site_summary (psi / occupancy probability / pointwise lppd and p_waic per unit, streamed over
     draws) against the oracle's per-site terms."""
@@ -292,7 +297,7 @@ def test_site_summary_streaming_kernel(name, dtype):
                            dtype=np.float32 if dtype == "float32" else np.float64, **g["model_kwargs"])
     with _make(g, dtype, prior=False) as lk:
         out = lk.site_summary(draws)
-    rn = g["model"] == "occu_rn"
+    rn = g["model"] in ("occu_rn", "nmixture")
     tol = 2e-5 if dtype == "float32" else 1e-6  # outputs are float32 either way
     a1 = out["abundance_mean" if rn else "psi_mean"].ravel()
     a2 = out["abundance_posterior_mean" if rn else "occupancy_prob"].ravel()
