@@ -18,6 +18,8 @@
 
 namespace bl {
 
+constexpr int kChainMaxKs = 8;  // runtime-Ks variants of the chain kernel hold up to 8 site coefficients
+
 template <int NS> struct VecLoad;
 template <> struct VecLoad<4> {
   static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) {
@@ -36,20 +38,28 @@ template <> struct VecLoad<2> {
 template <int KS, int KO, int NS, bool MASKED, int JT>
 __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const float* __restrict__ yfx,
                                            const float* __restrict__ mfx, const Layout& L, int n_valid,
-                                           const float (&b)[KS + 1], const float (&a)[KO + 1],
-                                           float (&acc)[3 + KS + KO], double& logp64) {
-  constexpr int KB = KS + 1;
+                                           const float (&b)[(KS < 0 ? kChainMaxKs : KS) + 1],
+                                           const float (&a)[KO + 1],
+                                           float (&acc)[3 + (KS < 0 ? kChainMaxKs : KS) + KO], double& logp64) {
+  // KS < 0: runtime number of site covariates (<= kChainMaxKs); the site-level loops are predicated on
+  // the warp-uniform k < ks and cost nothing in the visit loop
+  constexpr int KSM = KS < 0 ? kChainMaxKs : KS;
+  constexpr int KB = KSM + 1;
+  const int ks = KS < 0 ? L.ks : KS;
   const int J = JT > 0 ? JT : L.J;
   const float log_tiny = Num<float>::log_tiny();
   for (int g0 = 0; g0 < n_valid; g0 += NS) {
-    float x[KS > 0 ? KS : 1][NS], eta[NS];
+    float eta[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) eta[i] = b[0];
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      VecLoad<NS>::ld(tile + k * kWarp + g0, x[k]);
+    for (int k = 0; k < KSM; ++k) {
+      if (k < ks) {
+        float xk[NS];  // re-read (one broadcast LDS.128) for the gradient below instead of held in registers
+        VecLoad<NS>::ld(tile + k * kWarp + g0, xk);
 #pragma unroll
-      for (int i = 0; i < NS; ++i) eta[i] = fmaf(x[k][i], b[1 + k], eta[i]);
+        for (int i = 0; i < NS; ++i) eta[i] = fmaf(xk[i], b[1 + k], eta[i]);
+      }
     }
     float L1[NS], ga0[NS], ga[KO > 0 ? KO : 1][NS];
 #pragma unroll
@@ -86,6 +96,7 @@ __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const
     }
     float n1[NS];
     VecLoad<NS>::ld(tile + L.off_n1 * kWarp + g0, n1);
+    float geta[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       const float vf = (g0 + i < n_valid) ? 1.f : 0.f;
@@ -100,21 +111,31 @@ __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const
       const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
       const float r = rr * vf;
       const float ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv)) * vf;
-      const float geta = se.inr ? (rr - se.p) * vf : 0.f;
+      geta[i] = se.inr ? (rr - se.p) * vf : 0.f;
       logp64 += (double)ell;  // fp64 per unit: NUTS needs energy *differences* of a ~1e6-sized sum
-      acc[1] += geta;
-#pragma unroll
-      for (int k = 0; k < KS; ++k) acc[2 + k] = fmaf(geta, x[k][i], acc[2 + k]);
+      acc[1] += geta[i];
       acc[1 + KB] = fmaf(r, ga0[i], acc[1 + KB]);
 #pragma unroll
       for (int k = 0; k < KO; ++k) acc[2 + KB + k] = fmaf(r, ga[k][i], acc[2 + KB + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < KSM; ++k) {
+      if (k < ks) {
+        float xk[NS];
+        VecLoad<NS>::ld(tile + k * kWarp + g0, xk);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc[2 + k] = fmaf(geta[i], xk[i], acc[2 + k]);
+      }
     }
   }
 }
 
 template <int KS, int KO, int NS, int MINB, int BT, int JT>
 __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p) {
-  constexpr int KB = KS + 1, KA = KO + 1, NQ = 1 + KB + KA;
+  // accumulator slots: [0] unused, [1 .. KB] beta (KB = KSM + 1 slots, ks + 1 used), then KA alpha slots
+  constexpr int KSM = KS < 0 ? kChainMaxKs : KS;
+  constexpr int KB = KSM + 1, KA = KO + 1, NQ = 1 + KB + KA;
+  const int ks = KS < 0 ? p.L.ks : KS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
@@ -142,9 +163,9 @@ __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p
   {
     const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * p.D;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) b[k] = th[k];
+    for (int k = 0; k < KB; ++k) b[k] = (k <= ks) ? th[k] : 0.f;
 #pragma unroll
-    for (int k = 0; k < KA; ++k) a[k] = th[KB + k];
+    for (int k = 0; k < KA; ++k) a[k] = th[ks + 1 + k];
   }
   // fp64 running sums of the gradient live in shared memory ([q][tid], one column per thread): frees
   // 2 x (NQ-1) registers (measured: 10.4 -> 9.7 ms); the log-marginal stays in a register pair
@@ -195,10 +216,13 @@ __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p
     }
   }
   if (chain_ok) {
-    double* my = p.partial + ((size_t)blockIdx.x * p.C + c0 + tid) * NQ;
+    double* my = p.partial + ((size_t)blockIdx.x * p.C + c0 + tid) * p.NQ;
     my[0] = logp64;
 #pragma unroll
-    for (int i = 1; i < NQ; ++i) my[i] = g64[(size_t)i * BT];
+    for (int k = 0; k < KB; ++k)
+      if (k <= ks) my[1 + k] = g64[(size_t)(1 + k) * BT];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) my[2 + ks + k] = g64[(size_t)(1 + KB + k) * BT];
   }
   finish_block<float>(p, c0, ncb, &s_is_last);
 }
@@ -221,7 +245,9 @@ static cudaError_t launch_chain_one(const EvalParams& p, dim3 grid, size_t smem,
 bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32) return false;
   if (flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) return false;
-  return (ks == 1 && ko == 1) || (ks == 2 && ko == 1) || (ks == 5 && ko == 3);
+  // specialised (Ks, Ko) pairs, plus any Ks <= 8 with Ko in 1..4 through the runtime-Ks variants
+  return (ks == 1 && ko == 1) || (ks == 2 && ko == 1) || (ks == 5 && ko == 3) ||
+         (ks >= 0 && ks <= kChainMaxKs && ko >= 1 && ko <= 4);
 }
 
 // (NS, min blocks/SM) variants of the headline shape; BL_CHAIN_VARIANT picks one for tuning runs
@@ -237,7 +263,7 @@ static int chain_variant() {
 size_t occu_chain_smem(const Layout& L, int nstage, int block_threads) {
   size_t b = 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
   b = (b + 15) & ~size_t(15);
-  return b + (size_t)(3 + L.ks + L.ko) * block_threads * sizeof(double);  // fp64 gradient columns
+  return b + (size_t)(3 + kChainMaxKs + L.ko) * block_threads * sizeof(double);  // fp64 gradient columns
 }
 
 // threads per block (= chains per block) of the variant that launch_occu_chain will pick
@@ -259,6 +285,12 @@ cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaS
     if (v == 3) return launch_chain_one<5, 3, 4, 2, 256, 0>(p, grid, smem, st, occ);
     if (p.L.J == 8) return launch_chain_one<5, 3, 4, 2, 256, 8>(p, grid, smem, st, occ);
     return launch_chain_one<5, 3, 4, 2, 256>(p, grid, smem, st, occ);
+  }
+  if (ks >= 0 && ks <= kChainMaxKs) {  // runtime Ks
+    if (ko == 1) return launch_chain_one<-1, 1, 4, 2, 256>(p, grid, smem, st, occ);
+    if (ko == 2) return launch_chain_one<-1, 2, 4, 2, 256>(p, grid, smem, st, occ);
+    if (ko == 3) return launch_chain_one<-1, 3, 4, 2, 256>(p, grid, smem, st, occ);
+    if (ko == 4) return launch_chain_one<-1, 4, 4, 2, 256>(p, grid, smem, st, occ);
   }
   return cudaErrorNotSupported;
 }

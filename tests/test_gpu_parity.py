@@ -306,3 +306,28 @@ def test_site_summary_streaming_kernel(name, dtype):
     np.testing.assert_allclose(out["lppd"].ravel(), ref["lppd"], rtol=tol, atol=20 * tol)
     np.testing.assert_allclose(out["p_waic"].ravel(), ref["p_waic"], rtol=2e-3, atol=1e-5)
     assert abs(out["lppd_total"] - ref["lppd"].sum()) <= 1e-5 * abs(ref["lppd"].sum())
+
+
+@pytest.mark.parametrize("ks,ko", [(0, 1), (3, 2), (4, 4), (8, 3), (7, 1), (2, 2)])
+def test_chain_kernel_runtime_ks_variants(ks, ko):
+    """lane=chain occu kernel with a runtime number of site covariates (any Ks <= 8, Ko in 1..4)."""
+    import biolith_b200 as bb
+    from oracle import occupancy as orc
+
+    rng = np.random.default_rng(ks * 5 + ko)
+    S, J = 301, 9
+    X = rng.normal(size=(S, ks))
+    W = rng.normal(size=(S, 1, J, ko))
+    y = (rng.uniform(size=(1, S, 1, J)) < 0.35).astype(float)
+    y[0, rng.uniform(size=S) < 0.4] = 0.0
+    y[rng.uniform(size=y.shape) < 0.1] = np.nan
+    if ks:
+        X[5, 0] = np.nan
+    D = ks + ko + 2
+    th = rng.uniform(-2, 2, size=(140, D))
+    pr = orc.prepare(X, W, y)
+    idx = [0, 7, 139]
+    ref_lp, ref_gr = orc.logp_grad("occu", th[idx], pr)
+    with bb.OccupancyLikelihood("occu", X, W, y) as lk:
+        lp, gr = lk.logp_and_grad(th)
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"runtime-Ks chain ks={ks} ko={ko}")
