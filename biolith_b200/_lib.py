@@ -52,7 +52,7 @@ class bl_nuts_config(C.Structure):
     _fields_ = [
         ("n_chains", C.c_int32), ("num_warmup", C.c_int32), ("num_samples", C.c_int32),
         ("max_tree_depth", C.c_int32), ("adapt_step_size", C.c_int32), ("adapt_mass_matrix", C.c_int32),
-        ("seed", C.c_uint64), ("target_accept_prob", C.c_double), ("init_step_size", C.c_double),
+        ("find_heuristic_step_size", C.c_int32), ("reserved0", C.c_int32), ("seed", C.c_uint64), ("target_accept_prob", C.c_double), ("init_step_size", C.c_double),
         ("max_delta_energy", C.c_double),
     ]
 

@@ -33,6 +33,7 @@ struct NutsParams {
   double target_accept, max_delta_energy, init_step_size;
   unsigned long long seed;
   int adapt_step_size, adapt_mass;
+  int find_heuristic_step_size;  // numpyro HMC(find_heuristic_step_size=True): search at initialisation
   int n_windows;
   int win_end[kNutsMaxWindows];
   // device buffers
@@ -66,7 +67,7 @@ enum ScField {
 };
 enum IntField {
   I_IT, I_SAVED, I_DEPTH, I_NUM, I_TURN, I_DIV, I_SNUM, I_STURN, I_SDIV, I_RIGHT, I_DONE, I_WINDOW, I_SS_T,
-  I_CTR_LO, I_CTR_HI, I_LEAPS, I_LEAPS_WARM, I_COUNT
+  I_CTR_LO, I_CTR_HI, I_LEAPS, I_LEAPS_WARM, I_SEARCH, I_SEARCH_DIR, I_COUNT
 };
 
 // ---- Philox4x32-10 -----------------------------------------------------------------------
@@ -248,6 +249,38 @@ __device__ void adapt(const ChainView& cv, int t, double accept_prob) {
   }
 }
 
+// numpyro find_reasonable_step_size (hmc_util.py): single leapfrogs from the current point with fresh
+// momentum, doubling / halving the step size until the direction of "accept_prob vs target" flips.
+// I_SEARCH = 1 while searching; I_SEARCH_DIR = last direction (0 = none yet).
+template <typename T>
+__device__ void search_next_leaf(const ChainView& cv, Philox& rng) {
+  const NutsParams& p = cv.p;
+  double kin = 0.0;
+  for (int d = 0; d < p.D; d += 2) {
+    double n0, n1;
+    rng.normal2(n0, n1);
+    const double r0 = n0 * rsqrt(cv.v(V_IMM, d));
+    cv.v(V_RL, d) = r0;
+    kin += 0.5 * cv.v(V_IMM, d) * r0 * r0;
+    if (d + 1 < p.D) {
+      const double r1 = n1 * rsqrt(cv.v(V_IMM, d + 1));
+      cv.v(V_RL, d + 1) = r1;
+      kin += 0.5 * cv.v(V_IMM, d + 1) * r1 * r1;
+    }
+  }
+  cv.s(S_E0) = cv.s(S_U) + kin;
+  const double de = cv.s(S_EPS);
+  cv.s(S_DIREPS) = de;
+  T* th = reinterpret_cast<T*>(p.theta) + (size_t)p.slot[cv.c] * p.D;
+  for (int d = 0; d < p.D; ++d) {
+    const double rh = cv.v(V_RL, d) + 0.5 * de * cv.v(V_G, d);
+    const double zn = cv.v(V_Z, d) + de * cv.v(V_IMM, d) * rh;
+    cv.v(V_RHALF, d) = rh;
+    cv.v(V_ZNEW, d) = zn;
+    th[d] = (T)zn;
+  }
+}
+
 // First call: (logp, grad) at the initial positions are in place; set up every chain.
 template <typename T>
 __global__ void nuts_start_kernel(NutsParams p) {
@@ -271,8 +304,14 @@ __global__ void nuts_start_kernel(NutsParams p) {
   cv.s(S_SS_XT) = 0.0; cv.s(S_SS_XAVG) = 0.0; cv.s(S_SS_GAVG) = 0.0; cv.s(S_WN) = 0.0;
   cv.i(I_IT) = 0; cv.i(I_SAVED) = 0; cv.i(I_DONE) = 0; cv.i(I_WINDOW) = 0; cv.i(I_SS_T) = 0;
   cv.i(I_LEAPS) = 0; cv.i(I_LEAPS_WARM) = 0;
-  start_transition(cv, rng);
-  set_next_leaf<T>(cv);
+  cv.i(I_SEARCH) = 0; cv.i(I_SEARCH_DIR) = 0;
+  if (p.find_heuristic_step_size && p.adapt_step_size && p.num_warmup > 0) {
+    cv.i(I_SEARCH) = 1;
+    search_next_leaf<T>(cv, rng);
+  } else {
+    start_transition(cv, rng);
+    set_next_leaf<T>(cv);
+  }
   cv.i(I_CTR_LO) = (int)(unsigned int)rng.ctr;
   cv.i(I_CTR_HI) = (int)(unsigned int)(rng.ctr >> 32);
 }
@@ -289,6 +328,36 @@ __global__ void nuts_advance_kernel(NutsParams p) {
   const bool warm = cv.i(I_IT) < p.num_warmup;
   cv.i(I_LEAPS) += 1;
   if (warm) cv.i(I_LEAPS_WARM) += 1;
+  if (cv.i(I_SEARCH)) {
+    // one search leapfrog finished: delta energy -> direction; continue while the direction repeats
+    const int row_s = p.slot[c];
+    const T* gs = reinterpret_cast<const T*>(p.grad) + (size_t)row_s * D;
+    const double de_s = cv.s(S_DIREPS);
+    double kin_s = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double rn = cv.v(V_RHALF, d) + 0.5 * de_s * (double)gs[d];
+      kin_s += 0.5 * cv.v(V_IMM, d) * rn * rn;
+    }
+    double delta_s = (-p.logp[row_s] + kin_s) - cv.s(S_E0);
+    if (isnan(delta_s)) delta_s = INFINITY;
+    const int dir = (p.target_accept < exp(-delta_s)) ? 1 : -1;
+    const int last = cv.i(I_SEARCH_DIR);
+    double eps = cv.s(S_EPS);
+    if ((last == 0 || dir == last) && eps > 1e-30 && eps < 1e30) {
+      eps *= (dir > 0) ? 2.0 : 0.5;
+      cv.s(S_EPS) = eps;
+      cv.i(I_SEARCH_DIR) = dir;
+      search_next_leaf<T>(cv, rng);
+    } else {
+      cv.i(I_SEARCH) = 0;
+      cv.s(S_SS_PROX) = log(10.0 * eps);  // ss_init(log(10 * step_size))
+      start_transition(cv, rng);
+      set_next_leaf<T>(cv);
+    }
+    cv.i(I_CTR_LO) = (int)(unsigned int)rng.ctr;
+    cv.i(I_CTR_HI) = (int)(unsigned int)(rng.ctr >> 32);
+    return;
+  }
 
   // ---- 1. finish the leapfrog at z_new, build the leaf (numpyro _build_basetree)
   const int row = p.slot[c];
@@ -550,6 +619,7 @@ int bl_nuts_create(bl_dataset* ds, const bl_nuts_config* cfg, const void* theta0
   p.init_step_size = cfg->init_step_size > 0 ? cfg->init_step_size : 1.0;
   p.seed = cfg->seed;
   p.adapt_step_size = cfg->adapt_step_size; p.adapt_mass = cfg->adapt_mass_matrix;
+  p.find_heuristic_step_size = cfg->find_heuristic_step_size;
   std::vector<int> ends;
   build_schedule(p.num_warmup, ends);
   if ((int)ends.size() > kNutsMaxWindows) { delete s; return fail(BL_ERR_INVALID, "too many adaptation windows"); }

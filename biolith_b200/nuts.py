@@ -19,7 +19,8 @@ class NutsSampler:
     def __init__(self, likelihood: OccupancyLikelihood, num_chains: int, num_warmup: int = 1000,
                  num_samples: int = 1000, *, seed: int = 0, init_params: Optional[np.ndarray] = None,
                  init_radius: float = 2.0, max_tree_depth: int = 10, target_accept_prob: float = 0.8,
-                 step_size: float = 1.0, adapt_step_size: bool = True, adapt_mass_matrix: bool = True):
+                 step_size: float = 1.0, adapt_step_size: bool = True, adapt_mass_matrix: bool = True,
+                 find_heuristic_step_size: bool = False):
         self._lib = _lib.load()
         self.lk = likelihood
         self.num_chains, self.num_warmup, self.num_samples = int(num_chains), int(num_warmup), int(num_samples)
@@ -32,7 +33,8 @@ class NutsSampler:
             raise ValueError(f"init_params must have shape ({num_chains}, {D})")
         cfg = bl_nuts_config(
             n_chains=num_chains, num_warmup=num_warmup, num_samples=num_samples, max_tree_depth=max_tree_depth,
-            adapt_step_size=int(adapt_step_size), adapt_mass_matrix=int(adapt_mass_matrix), seed=seed,
+            adapt_step_size=int(adapt_step_size), adapt_mass_matrix=int(adapt_mass_matrix),
+            find_heuristic_step_size=int(find_heuristic_step_size), reserved0=0, seed=seed,
             target_accept_prob=target_accept_prob, init_step_size=step_size, max_delta_energy=1000.0)
         self._h = C.c_void_p()
         check(self._lib.bl_nuts_create(likelihood.handle, C.byref(cfg), th0.ctypes.data, C.byref(self._h)),

@@ -132,3 +132,23 @@ def test_fit_nmixture_recovers_truth():
     N_true = true["N"][0, 0, :]
     assert np.corrcoef(ss["abundance_posterior_mean"][:, 0], N_true)[0, 1] > 0.8
     assert np.all(res.mcmc.summary()["beta"]["r_hat"] < 1.05)
+
+
+def test_find_heuristic_step_size_option():
+    """numpyro's HMC(find_heuristic_step_size=True) analogue: same posterior, different warm-up start."""
+    import biolith_b200 as bb
+    from biolith_b200 import diagnostics as dg
+
+    g = load_golden("occu_default")
+    d = g["data"]
+    with bb.OccupancyLikelihood("occu", d["site_covs"], d["obs_covs"], d["obs"], max_chains=32) as lk:
+        out = []
+        for flag in (False, True):
+            s = bb.NutsSampler(lk, 32, 300, 300, seed=3, find_heuristic_step_size=flag)
+            assert s.run(timeout=120)
+            out.append(s.results()["samples"].astype(np.float64))
+            s.close()
+    a, b = out
+    se = np.sqrt(dg.mcse_mean(a) ** 2 + dg.mcse_mean(b) ** 2)
+    assert np.all(np.abs(a.reshape(-1, 4).mean(0) - b.reshape(-1, 4).mean(0)) < 5 * se)
+    assert np.all(dg.split_gelman_rubin(b) < 1.03)
