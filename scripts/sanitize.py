@@ -1,19 +1,26 @@
-"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck).
+usage: sanitize.py [model ...]   (default: all four)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import biolith_b200 as bb
 
 rng = np.random.default_rng(0)
-for model, kw in (("occu", {}), ("occu_rn", dict(max_abundance=20)), ("occu_cop", dict(false_positives_constant=True))):
-    data, _ = bb.simulate_occupancy(model, n_site_covs=5, n_obs_covs=3, n_sites=333, deployment_days_per_site=56,
+ALL = {"occu": {}, "occu_rn": dict(max_abundance=12), "occu_cop": dict(false_positives_constant=True),
+       "nmixture": dict(max_abundance=80)}
+todo = sys.argv[1:] or list(ALL)
+S = int(os.environ.get("SANITIZE_SITES", "333"))
+for model in todo:
+    kw = ALL[model]
+    data, _ = bb.simulate_occupancy(model, n_site_covs=5, n_obs_covs=3, n_sites=S, deployment_days_per_site=56,
                                     simulate_missing=True, random_seed=1)
     T = data.get("session_duration")
     with bb.OccupancyLikelihood(model, data["site_covs"], data["obs_covs"], data["obs"], T, **kw) as lk:
         for C in (3, 130):  # site-parallel engine, chain-parallel kernels
             lp, gr = lk.logp_and_grad(rng.uniform(-1, 1, size=(C, lk.theta_dim)))
             assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr))
+        lk.site_summary(rng.uniform(-1, 1, size=(5, lk.theta_dim)))
         s = bb.NutsSampler(lk, 130, 6, 4, seed=1)
-        s.run(max_steps=400)
+        s.run(max_steps=200)
         s.close()
-    print(model, "ok")
+    print(model, "ok", flush=True)
