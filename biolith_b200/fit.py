@@ -99,7 +99,8 @@ def fit(
     if init_strategy is not None:
         raise BiolithB200Error(-2, "fit", "custom init_strategy is not supported (init_to_uniform(radius=2) is used)")
     for k, default in REJECTED_IF_SET.items():
-        if kwargs.get(k, default) not in (default, None, False):
+        v = kwargs.get(k, default)
+        if v is not None and v is not False and v is not default:
             raise BiolithB200Error(-2, "fit", f"{k} is outside the accelerated path (no fallback)")
     for k in ("regressor_occ", "regressor_det", "regressor_abu"):
         r = kwargs.get(k)
