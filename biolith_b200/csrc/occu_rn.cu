@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
   const int tid = threadIdx.x;
   double* g64 = reinterpret_cast<double*>(mfx + (size_t)J * kWarp) + tid;      // [NQ][BT]
   float* A = reinterpret_cast<float*>(g64 - tid + (size_t)NQ * BT) + tid;      // [K+1][BT]
+  float* U0 = A - tid + (size_t)(K + 1) * BT + tid;                            // [J][BT] log(1-r_j) of non-detections
   const int c0 = blockIdx.y * p.CB;
   const int ncb = min(p.CB, p.C - c0);
   const bool chain_ok = tid < ncb;
@@ -349,8 +350,9 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
       }
       const float logZp = Mp + M::log_(Zp);
       Ep *= M::rcp_(Zp);
-      // ---- pass 1
-      float Utot = 0.f, n0 = 0.f;
+      // ---- pass 1: detections run the k-loop; non-detections only record u_j = log(1-r_j)
+      float Utot = 0.f, umin = 0.f;
+      int n0i = 0;
       for (int j = 0; j < J; ++j) {
         if (mfx[j * kWarp + si] == 0.f) continue;  // warp-uniform
         float nu = a[0];
@@ -361,14 +363,9 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         const float u = -sp;
         if (yfx[j * kWarp + si] == 0.f) {  // warp-uniform
           Utot += u;
-          n0 += 1.f;
-          float kd = (float)K;
-          for (int k = K; k >= 0; --k) {  // clamped tail states only: replace k u + log(1-c) by log eps
-            const float lq = fmaf(kd, u, l1mc);
-            if (lq > log_eps) break;
-            A[(size_t)k * BT] += log_eps - lq;
-            kd -= 1.f;
-          }
+          umin = fminf(umin, u);
+          U0[(size_t)n0i * BT] = u;
+          ++n0i;
         } else {
           const float qv = 1.f - r;
           float qk = 1.f, P0 = 0.f, kk = 0.f;
@@ -386,9 +383,22 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
           }
         }
       }
+      // non-detections are linear in k except on the clamped tail (k u_j + log(1-c) <= log eps): one
+      // descending k-loop adds max(log eps - lq_kj, 0) over all of them and stops at the first state
+      // where no visit is clamped (lq grows as k falls)
+      if (fmaf((float)K, umin, l1mc) <= log_eps) {
+        float kd = (float)K;
+        for (int k = K; k >= 0; --k) {
+          float corr = 0.f;
+          for (int i = 0; i < n0i; ++i) corr += fmaxf(log_eps - fmaf(kd, U0[(size_t)i * BT], l1mc), 0.f);
+          if (corr == 0.f) break;
+          A[(size_t)k * BT] += corr;
+          kd -= 1.f;
+        }
+      }
       // ---- posterior over N (adds the linear non-detection part k U + n0 log(1-c)); the weights stay
       // unnormalised (e_k = exp(A_k - max)) and the sums are scaled by 1/Z afterwards
-      const float off0 = n0 * l1mc;
+      const float off0 = (float)n0i * l1mc;
       float Mx = -N::inf();
       kf = 0.f;
 #pragma unroll 4
@@ -411,12 +421,12 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
       const float iZ = M::rcp_(Z);
       const float ell = (Mx + M::log_(Z)) - logZp;
       const float geta = Eqn * iZ - Ep;
-      // ---- pass 2 (sums over the unnormalised weights, scaled by 1/Z per visit)
+      // ---- pass 2 (sums over the unnormalised weights, scaled by 1/Z per visit).  Sweep 1: detections.
       float ga0 = 0.f, gc = 0.f, ga[KO > 0 ? KO : 1];
 #pragma unroll
       for (int k = 0; k < KO; ++k) ga[k] = 0.f;
       for (int j = 0; j < J; ++j) {
-        if (mfx[j * kWarp + si] == 0.f) continue;
+        if (mfx[j * kWarp + si] == 0.f || yfx[j * kWarp + si] == 0.f) continue;
         float w[KO > 0 ? KO : 1];
         float nu = a[0];
 #pragma unroll
@@ -427,8 +437,64 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         float sp, r;
         M::softsig(nu, sp, r);
         const float u = -sp;
-        float g, gcj;
-        if (yfx[j * kWarp + si] == 0.f) {
+        const float qv = 1.f - r;
+        float qk = 1.f, P0 = 0.f, kk = 0.f, g = 0.f, gcj = 0.f;
+#pragma unroll 4
+        for (int k = 0; k <= K; ++k) {
+          const float lq = fmaf(kk, u, l1mc);
+          const float P = fmaf(omc, P0, cval);
+          const bool inr = (P > -N::neg_tiny()) && (lq > log_eps);
+          float dt = -(omc * qk) * M::rcp_(P);  // dt/dlq = -(1-P)/P, 1-P = (1-c) q^k
+          dt = inr ? dt : 0.f;
+          const float wd = A[(size_t)k * BT] * dt;
+          g = fmaf(kk, wd, g);
+          gcj += wd;
+          P0 = fmaf(qk, r, P0);
+          qk *= qv;
+          kk += 1.f;
+        }
+        const float gnu = -r * g * iZ;  // dlq/dnu = -k r
+        ga0 += gnu;
+#pragma unroll
+        for (int k = 0; k < KO; ++k) ga[k] = fmaf(gnu, w[k], ga[k]);
+        gc = fmaf(gcj, iZ, gc);
+      }
+      // Sweep 2: non-detections need sum_{k <= kc_j} k e_k (kc_j = last unclamped state): turn the
+      // column into that prefix sum in place and look it up per visit.  With a false-positive constant
+      // the k-unweighted prefix is needed too and the (rare) tail loop is kept instead.
+      if (!fpc) {
+        float run = 0.f;
+        kf = 0.f;
+#pragma unroll 4
+        for (int k = 0; k <= K; ++k) {
+          run = fmaf(kf, A[(size_t)k * BT], run);
+          A[(size_t)k * BT] = run;
+          kf += 1.f;
+        }
+      }
+      for (int j = 0; j < J; ++j) {
+        if (mfx[j * kWarp + si] == 0.f || yfx[j * kWarp + si] != 0.f) continue;
+        float w[KO > 0 ? KO : 1];
+        float nu = a[0];
+#pragma unroll
+        for (int k = 0; k < KO; ++k) {
+          w[k] = tile[(p.L.off_w + j * KO + k) * kWarp + si];
+          nu = fmaf(w[k], a[1 + k], nu);
+        }
+        float sp, r;
+        M::softsig(nu, sp, r);
+        const float u = -sp;
+        float g, gcj = 0.f;
+        if (!fpc) {
+          // kc = largest k with k u + log(1-c) > log eps, decided by the same fmaf as pass 1
+          int kc = K;
+          if (fmaf((float)K, u, l1mc) <= log_eps) {
+            kc = (int)fminf((log_eps - l1mc) / u, (float)K);  // u < 0 here
+            while (kc < K && fmaf((float)(kc + 1), u, l1mc) > log_eps) ++kc;
+            while (kc >= 0 && !(fmaf((float)kc, u, l1mc) > log_eps)) --kc;
+          }
+          g = kc >= 0 ? A[(size_t)kc * BT] : 0.f;
+        } else {
           float tk = 0.f, t0 = 0.f, kd = (float)K;  // (k-weighted) weight of the clamped tail states
           for (int k = K; k >= 0; --k) {
             const float lq = fmaf(kd, u, l1mc);
@@ -440,26 +506,8 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
           }
           g = Eqn - tk;
           gcj = Z - t0;
-        } else {
-          const float qv = 1.f - r;
-          float qk = 1.f, P0 = 0.f, kk = 0.f;
-          g = 0.f; gcj = 0.f;
-#pragma unroll 4
-          for (int k = 0; k <= K; ++k) {
-            const float lq = fmaf(kk, u, l1mc);
-            const float P = fmaf(omc, P0, cval);
-            const bool inr = (P > -N::neg_tiny()) && (lq > log_eps);
-            float dt = -(omc * qk) * M::rcp_(P);  // dt/dlq = -(1-P)/P, 1-P = (1-c) q^k
-            dt = inr ? dt : 0.f;
-            const float wd = A[(size_t)k * BT] * dt;
-            g = fmaf(kk, wd, g);
-            gcj += wd;
-            P0 = fmaf(qk, r, P0);
-            qk *= qv;
-            kk += 1.f;
-          }
         }
-        const float gnu = -r * g * iZ;  // dlq/dnu = -k r
+        const float gnu = -r * g * iZ;
         ga0 += gnu;
 #pragma unroll
         for (int k = 0; k < KO; ++k) ga[k] = fmaf(gnu, w[k], ga[k]);
@@ -507,7 +555,7 @@ size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D) {
   size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
   bts = (bts + 15) & ~size_t(15);
   bts += (size_t)(1 + D) * kRnChainThreads * sizeof(double);
-  return bts + (size_t)(K + 1) * kRnChainThreads * sizeof(float);
+  return bts + (size_t)(K + 1 + L.J) * kRnChainThreads * sizeof(float);
 }
 
 template <int KS, int KO>
