@@ -156,7 +156,10 @@ struct OccuCopModel {
 // ------------------------------------------------------------------------------------------------
 template <int KS, int KO, int BT, int JT>
 __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams p) {
-  constexpr int KB = KS + 1, KA = KO + 1, NS = 4, NQM = 1 + KB + KA + 2;
+  // KS < 0: runtime number of site covariates (<= 8); accumulator slots are laid out for the capacity
+  constexpr int KSM = KS < 0 ? 8 : KS;
+  constexpr int KB = KSM + 1, KA = KO + 1, NS = 4, NQM = 1 + KB + KA + 2;
+  const int ks = KS < 0 ? p.L.ks : KS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
@@ -185,10 +188,10 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
   {
     const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * D;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) b[k] = th[k];
+    for (int k = 0; k < KB; ++k) b[k] = (k <= ks) ? th[k] : 0.f;
 #pragma unroll
-    for (int k = 0; k < KA; ++k) a[k] = th[KB + k];
-    int i = KB + KA;
+    for (int k = 0; k < KA; ++k) a[k] = th[ks + 1 + k];
+    int i = ks + 1 + KA;
     if (fpc) c = expf(th[i++]);
     if (fpu) u = expf(th[i++]);
   }
@@ -218,15 +221,17 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
 #pragma unroll
     for (int i = 0; i < NQM; ++i) acc[i] = 0.f;
     for (int g0 = 0; g0 < n_valid; g0 += NS) {
-      float x[KS > 0 ? KS : 1][NS], eta[NS];
+      float eta[NS], geta[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) eta[i] = b[0];
 #pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(tile + k * kWarp + g0);
-        x[k][0] = v.x; x[k][1] = v.y; x[k][2] = v.z; x[k][3] = v.w;
+      for (int k = 0; k < KSM; ++k) {
+        if (k < ks) {  // re-read below for the gradient instead of held in registers
+          const float4 v = *reinterpret_cast<const float4*>(tile + k * kWarp + g0);
+          const float xk[NS] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < NS; ++i) eta[i] = fmaf(x[k][i], b[1 + k], eta[i]);
+          for (int i = 0; i < NS; ++i) eta[i] = fmaf(xk[i], b[1 + k], eta[i]);
+        }
       }
       float L1[NS], s1[NS], ga0[NS], ga[KO > 0 ? KO : 1][NS];
 #pragma unroll
@@ -290,17 +295,24 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
           ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv));
         }
         const float r = rr * vf;
-        const float geta = se.inr ? (rr - se.p) * vf : 0.f;
+        geta[i] = se.inr ? (rr - se.p) * vf : 0.f;
         const float w0 = (rr < 1.f) ? (1.f - rr) * d0 * vf : 0.f;
         logp64 += (double)(ell * vf);
-        acc[1] += geta;
-#pragma unroll
-        for (int k = 0; k < KS; ++k) acc[2 + k] = fmaf(geta, x[k][i], acc[2 + k]);
+        acc[1] += geta[i];
         acc[1 + KB] = fmaf(r, ga0[i], acc[1 + KB]);
 #pragma unroll
         for (int k = 0; k < KO; ++k) acc[2 + KB + k] = fmaf(r, ga[k][i], acc[2 + KB + k]);
         acc[1 + KB + KA] += fmaf(r, s1[i], w0);  // dl/dc (constant fp): both branches
         acc[2 + KB + KA] += w0;                  // dl/du (unoccupied fp): z = 0 branch only
+      }
+#pragma unroll
+      for (int k = 0; k < KSM; ++k) {
+        if (k < ks) {
+          const float4 v = *reinterpret_cast<const float4*>(tile + k * kWarp + g0);
+          const float xk[NS] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < NS; ++i) acc[2 + k] = fmaf(geta[i], xk[i], acc[2 + k]);
+        }
       }
     }
 #pragma unroll
@@ -315,8 +327,12 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
   if (chain_ok) {
     double* my = p.partial + ((size_t)blockIdx.x * p.C + c0 + tid) * NQ;
     my[0] = logp64;
-    for (int i = 1; i < 1 + KB + KA; ++i) my[i] = g64[(size_t)i * BT];
-    int i = 1 + KB + KA;
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk)
+      if (kk <= ks) my[1 + kk] = g64[(size_t)(1 + kk) * BT];
+#pragma unroll
+    for (int kk = 0; kk < KA; ++kk) my[2 + ks + kk] = g64[(size_t)(1 + KB + kk) * BT];
+    int i = 2 + ks + KA;
     const double gc = g64[(size_t)(1 + KB + KA) * BT], gu = g64[(size_t)(2 + KB + KA) * BT];
     if (fpc) my[i++] = gc * (double)c;  // x = log c: dc/dx = c
     if (fpu) my[i++] = gu * (double)u;
@@ -328,7 +344,7 @@ constexpr int kCopChainThreads = 256;
 
 bool occu_cop_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
-  return (ks == 1 && ko == 1) || (ks == 5 && ko == 3);
+  return (ks == 5 && ko == 3) || (ks >= 0 && ks <= 8 && ko >= 1 && ko <= 4);
 }
 
 int occu_cop_chain_block_threads() { return kCopChainThreads; }
@@ -336,7 +352,7 @@ int occu_cop_chain_block_threads() { return kCopChainThreads; }
 size_t occu_cop_chain_smem(const Layout& L, int nstage) {
   size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float);
   bts = (bts + 15) & ~size_t(15);
-  return bts + (size_t)(5 + L.ks + L.ko) * kCopChainThreads * sizeof(double);
+  return bts + (size_t)(5 + 8 + L.ko) * kCopChainThreads * sizeof(double);
 }
 
 template <int KS, int KO, int JT>
@@ -354,10 +370,15 @@ static cudaError_t launch_cop_chain_one(const EvalParams& p, dim3 grid, size_t s
 }
 
 cudaError_t launch_occu_cop_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  if (p.L.ks == 1 && p.L.ko == 1) return launch_cop_chain_one<1, 1, 0>(p, grid, smem, st, occ);
   if (p.L.ks == 5 && p.L.ko == 3) {
     if (p.L.J == 12) return launch_cop_chain_one<5, 3, 12>(p, grid, smem, st, occ);
     return launch_cop_chain_one<5, 3, 0>(p, grid, smem, st, occ);
+  }
+  if (p.L.ks >= 0 && p.L.ks <= 8) {  // runtime Ks
+    if (p.L.ko == 1) return launch_cop_chain_one<-1, 1, 0>(p, grid, smem, st, occ);
+    if (p.L.ko == 2) return launch_cop_chain_one<-1, 2, 0>(p, grid, smem, st, occ);
+    if (p.L.ko == 3) return launch_cop_chain_one<-1, 3, 0>(p, grid, smem, st, occ);
+    if (p.L.ko == 4) return launch_cop_chain_one<-1, 4, 0>(p, grid, smem, st, occ);
   }
   return cudaErrorNotSupported;
 }

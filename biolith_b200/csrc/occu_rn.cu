@@ -239,11 +239,14 @@ struct OccuRnModel {
 // the clamp binds (k u_j + log(1-c) <= log eps), so they are folded into one slope U = sum u_j plus a
 // short descending correction loop over the clamped tail states only.
 // ------------------------------------------------------------------------------------------------
-template <int KS, int KO, int BT>
+// RT = true: KS / KO are capacities and the actual covariate counts come from the layout (the k-loops
+// dominate, so the predicated site-level loops cost nothing measurable)
+template <int KS, int KO, int BT, bool RT>
 __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p) {
   using N = Num<float>;
   using M = Mth<float, true>;
   constexpr int KB = KS + 1, KA = KO + 1;
+  const int ks = RT ? p.L.ks : KS, ko = RT ? p.L.ko : KO;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
@@ -276,9 +279,9 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
   {
     const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * D;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) b[k] = th[k];
+    for (int k = 0; k < KB; ++k) b[k] = (k <= ks) ? th[k] : 0.f;
 #pragma unroll
-    for (int k = 0; k < KA; ++k) a[k] = th[KB + k];
+    for (int k = 0; k < KA; ++k) a[k] = (k <= ko) ? th[ks + 1 + k] : 0.f;
     if (fpc) {
       const float x = th[D - 1];
       cval = 1.f / (1.f + expf(-x));
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
       float eta = b[0];
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        x[k] = tile[k * kWarp + si];
+        x[k] = (k < ks) ? tile[k * kWarp + si] : 0.f;
         eta = fmaf(x[k], b[1 + k], eta);
       }
       // ---- prior logits k eta - lgamma(k+1) (the -lambda term cancels) and their normaliser.  The
@@ -357,7 +360,8 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         if (mfx[j * kWarp + si] == 0.f) continue;  // warp-uniform
         float nu = a[0];
 #pragma unroll
-        for (int k = 0; k < KO; ++k) nu = fmaf(tile[(p.L.off_w + j * KO + k) * kWarp + si], a[1 + k], nu);
+        for (int k = 0; k < KO; ++k)
+          if (k < ko) nu = fmaf(tile[(p.L.off_w + j * ko + k) * kWarp + si], a[1 + k], nu);
         float sp, r;
         M::softsig(nu, sp, r);
         const float u = -sp;
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         float nu = a[0];
 #pragma unroll
         for (int k = 0; k < KO; ++k) {
-          w[k] = tile[(p.L.off_w + j * KO + k) * kWarp + si];
+          w[k] = (k < ko) ? tile[(p.L.off_w + j * ko + k) * kWarp + si] : 0.f;
           nu = fmaf(w[k], a[1 + k], nu);
         }
         float sp, r;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
         float nu = a[0];
 #pragma unroll
         for (int k = 0; k < KO; ++k) {
-          w[k] = tile[(p.L.off_w + j * KO + k) * kWarp + si];
+          w[k] = (k < ko) ? tile[(p.L.off_w + j * ko + k) * kWarp + si] : 0.f;
           nu = fmaf(w[k], a[1 + k], nu);
         }
         float sp, r;
@@ -524,10 +528,12 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
     }
     g64[0] += logp_tile;
 #pragma unroll
-    for (int k = 0; k < KB; ++k) g64[(size_t)(1 + k) * BT] += (double)acc_gb[k];
+    for (int k = 0; k < KB; ++k)
+      if (k <= ks) g64[(size_t)(1 + k) * BT] += (double)acc_gb[k];
 #pragma unroll
-    for (int k = 0; k < KA; ++k) g64[(size_t)(1 + KB + k) * BT] += (double)acc_ga[k];
-    if (fpc) g64[(size_t)(1 + KB + KA) * BT] += (double)(-acc_gc * dcdx / omc);
+    for (int k = 0; k < KA; ++k)
+      if (k <= ko) g64[(size_t)(2 + ks + k) * BT] += (double)acc_ga[k];
+    if (fpc) g64[(size_t)(3 + ks + ko) * BT] += (double)(-acc_gc * dcdx / omc);
     __syncthreads();
     if (tid == 0 && it + p.nstage < n_it) {
       mbar_expect_tx(&bars[s], tile_bytes);
@@ -546,7 +552,7 @@ constexpr int kRnChainThreads = 256;
 
 bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
-  return (ks == 1 && ko == 1) || (ks == 5 && ko == 3);
+  return ks >= 0 && ks <= 8 && ko >= 0 && ko <= 4;  // (5,3) specialised, the rest through the capacity variant
 }
 
 int occu_rn_chain_block_threads() { return kRnChainThreads; }
@@ -558,9 +564,9 @@ size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D) {
   return bts + (size_t)(K + 1 + L.J) * kRnChainThreads * sizeof(float);
 }
 
-template <int KS, int KO>
+template <int KS, int KO, bool RT>
 static cudaError_t launch_rn_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = occu_rn_chain_kernel<KS, KO, kRnChainThreads>;
+  auto kern = occu_rn_chain_kernel<KS, KO, kRnChainThreads, RT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -579,8 +585,8 @@ cudaError_t launch_occu_rn_chain(const EvalParams& p, dim3 grid, size_t smem, cu
     cudaError_t e = ensure_lgamma_table();
     if (e != cudaSuccess) return e;
   }
-  if (p.L.ks == 1 && p.L.ko == 1) return launch_rn_chain_one<1, 1>(p, grid, smem, st, occ);
-  if (p.L.ks == 5 && p.L.ko == 3) return launch_rn_chain_one<5, 3>(p, grid, smem, st, occ);
+  if (p.L.ks == 5 && p.L.ko == 3) return launch_rn_chain_one<5, 3, false>(p, grid, smem, st, occ);
+  if (p.L.ks <= 8 && p.L.ko <= 4) return launch_rn_chain_one<8, 4, true>(p, grid, smem, st, occ);
   return cudaErrorNotSupported;
 }
 
