@@ -312,7 +312,7 @@ def main():
             line["nuts"] = nuts
         if not args.no_cpu_baseline and world == 1 and model == "occu":
             line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_finite(line)), flush=True)
     lk.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -365,6 +365,17 @@ def run_nuts(args, lk, chains, rank, world, shard, dist):
         "note": "wall includes warm-up; ESS = numpyro.diagnostics.effective_sample_size over all chains; "
                 "min/median over the %d parameters" % x.shape[2],
     }
+
+
+def _finite(o):
+    """strict JSON: non-finite floats (e.g. ESS of a chain that never moved) become null"""
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    if isinstance(o, float) and not np.isfinite(o):
+        return None
+    return o
 
 
 def shard_is_chains(workload):
