@@ -117,7 +117,14 @@ def make_data(workload, seed):
     from biolith_b200.simulate import simulate_occupancy
 
     model, kw, chains, shard = WORKLOADS[workload]
-    data, _ = simulate_occupancy(model, random_seed=seed, **kw)
+    if shard == "sites" and seed != 0:
+        # every site shard shares ONE truth (that of seed 0); the seed only varies covariates / latents.
+        # (Per-shard truths would make the pooled 16M-site posterior a product of 8 conflicting, extremely
+        # sharp likelihoods whose local modes trap chains: measured r-hat 13-24 on 8 GPUs.)
+        _, true0 = simulate_occupancy(model, random_seed=0, **{**kw, "n_sites": 2000})
+        data, _ = simulate_occupancy(model, random_seed=seed, beta=true0["beta"], alpha=true0["alpha"], **kw)
+    else:
+        data, _ = simulate_occupancy(model, random_seed=seed, **kw)
     X = data["site_covs"].astype(np.float32)   # the reference ingests as fp32 (utils/data.py:135-140)
     W = data["obs_covs"].astype(np.float32)
     y = data["obs"].astype(np.float32)
@@ -266,6 +273,31 @@ def main():
     value = chains_total * args.steps / (total_ms * 1e-3)
     e2e_value = chains_total * args.steps / e2e_s
 
+    exchange_check = None
+    if comm is not None:
+        # self-check of the cross-rank exchange: the fused / NCCL result must equal the fp64 sum of every
+        # rank's own shard evaluated on a plain (unattached) handle, and be bit-identical on all ranks
+        import torch
+
+        with bb.OccupancyLikelihood(model, X, W, y, make_data.session_duration, dtype=args.dtype, device=local_rank,
+                                    prior=False, **MODEL_KW.get(model, {})) as loc:
+            lp_loc, gr_loc = loc.logp_and_grad(theta[:64])
+        t = torch.tensor(np.concatenate([lp_loc.astype(np.float64)[:, None], gr_loc.astype(np.float64)], axis=1),
+                         dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        ref = t.cpu().numpy()
+        th64 = theta[:64].astype(np.float64)
+        ref[:, 0] += (-0.5 * th64 ** 2 - 0.9189385332046727).sum(axis=1)  # the handle under test adds N(0,1) priors
+        ref[:, 1:] -= th64
+        got = np.concatenate([lp_host.astype(np.float64)[:64, None], gr_host.astype(np.float64)[:64]], axis=1)
+        err = np.abs(got - ref) / np.maximum(np.abs(ref).max(axis=0, keepdims=True), 1.0)
+        g = torch.tensor(got, dtype=torch.float64, device="cuda")
+        gmax, gmin = g.clone(), g.clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+        exchange_check = {"max_rel_err_vs_sum_of_shards": float(err.max()),
+                          "bit_identical_across_ranks": bool(torch.equal(gmax, gmin)), "mode": args.exchange}
+
     nuts = None
     if not args.no_nuts:
         nuts = run_nuts(args, lk, chains, rank, world, shard, dist)
@@ -308,6 +340,8 @@ def main():
             line["roofline_sfu"] = {"bound": "sfu", "achieved": mufu / (ms_launch * 1e-3) / 1e12,
                                     "peak": peak_mufu / 1e12, "unit": "T MUFU/s", "frac": mufu / (ms_launch * 1e-3) / peak_mufu,
                                     "note": "secondary roofline: the kernel is issue/SFU bound, not HBM bound"}
+        if exchange_check is not None:
+            line["exchange_check"] = exchange_check
         if nuts is not None:
             line["nuts"] = nuts
         if not args.no_cpu_baseline and world == 1 and model == "occu":

@@ -96,8 +96,9 @@ def fit(
         raise BiolithB200Error(-2, "fit", f"model {name!r} is outside the accelerated path {sorted(SUPPORTED)}")
     if kernel not in (None, "nuts"):
         raise BiolithB200Error(-2, "fit", f"kernel={kernel!r}: only NUTS is implemented on the device")
-    if init_strategy is not None:
-        raise BiolithB200Error(-2, "fit", "custom init_strategy is not supported (init_to_uniform(radius=2) is used)")
+    if init_strategy is not None and init_strategy != "map":
+        raise BiolithB200Error(-2, "fit", "init_strategy: only None (init_to_uniform(radius=2), the reference's default) "
+                               "or \"map\" (start at the posterior mode, biolith_b200.optim) are supported")
     for k, default in REJECTED_IF_SET.items():
         v = kwargs.get(k, default)
         if v is not None and v is not False and v is not default:
@@ -135,7 +136,8 @@ def fit(
         # species are independent problems sharing the covariates (one handle each, occu.py:182-186)
         parts.append(_fit_one(name, site_covs, obs_covs, obs_np4[sp:sp + 1], session_duration, fpc, fpu, kwargs,
                               dtype, device, num_chains, num_warmup, num_samples, random_seed + 7919 * sp,
-                              max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods))
+                              max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods,
+                              init_strategy))
     grouped = {}
     for k in parts[0][0]:
         ax = 2 if k in ("beta", "alpha") else -1
@@ -155,13 +157,20 @@ def fit(
 
 
 def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs, dtype, device, num_chains,
-             num_warmup, num_samples, seed, max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods):
+             num_warmup, num_samples, seed, max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods,
+             init_strategy=None):
     """One species: pack, sample on the device, return (grouped samples, extra fields, info)."""
     lk = OccupancyLikelihood(
         name, site_covs, obs_covs, obs, session_duration, false_positives_constant=fpc,
         false_positives_unoccupied=fpu, max_abundance=kwargs.get("max_abundance", 100), dtype=dtype, prior=True,
         device=device, max_chains=num_chains, **prior_kw)
-    sampler = NutsSampler(lk, num_chains, num_warmup, num_samples, seed=seed,
+    init_params = None
+    if init_strategy == "map":
+        from .optim import find_map, init_around
+
+        theta_map, _, _ = find_map(lk, seed=seed)
+        init_params = init_around(theta_map, num_chains, seed=seed)
+    sampler = NutsSampler(lk, num_chains, num_warmup, num_samples, seed=seed, init_params=init_params,
                           max_tree_depth=max_tree_depth, target_accept_prob=target_accept_prob)
     complete = sampler.run(timeout=timeout)
     if not complete:

@@ -13,11 +13,19 @@ ap.add_argument("--samples", type=int, default=100)
 ap.add_argument("--timeout", type=float, default=300)
 ap.add_argument("--depth", type=int, default=10)
 ap.add_argument("--heuristic", action="store_true")
+ap.add_argument("--map-init", action="store_true")
 a = ap.parse_args()
 data, true = bb.simulate_occupancy("occu", n_site_covs=5, n_obs_covs=3, n_sites=a.sites, deployment_days_per_site=56)
 X, W, y = (data[k].astype(np.float32) for k in ("site_covs", "obs_covs", "obs"))
 lk = bb.OccupancyLikelihood("occu", X, W, y, max_chains=a.chains)
-s = bb.NutsSampler(lk, a.chains, a.warmup, a.samples, seed=1, max_tree_depth=a.depth,
+init = None
+if a.map_init:
+    from biolith_b200.optim import find_map, init_around
+    t0 = time.perf_counter()
+    th_map, lp_map, info = find_map(lk, verbose=True)
+    print('map search', round(time.perf_counter() - t0, 2), 's  |grad|inf', info['grad_inf_norm'], 'theta', th_map.round(4).tolist())
+    init = init_around(th_map, a.chains)
+s = bb.NutsSampler(lk, a.chains, a.warmup, a.samples, seed=1, max_tree_depth=a.depth, init_params=init,
                    find_heuristic_step_size=a.heuristic)
 t0 = time.perf_counter()
 ok = s.run(timeout=a.timeout)

@@ -14,6 +14,7 @@ def _data():
 @pytest.mark.parametrize("kw", [
     dict(kernel="hmc"), dict(kernel="discrete_hmc_gibbs"), dict(site_random_effects=True),
     dict(obs_random_effects=True), dict(coords=np.zeros((6, 2))), dict(init_strategy=lambda *a: None),
+    dict(init_strategy="median"),
 ])
 def test_options_outside_the_path_raise(kw):
     import biolith_b200 as bb

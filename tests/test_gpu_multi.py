@@ -59,10 +59,11 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("mode", ["nccl", "p2p"])
-def test_site_sharded_two_ranks(mode):
-    if _n_gpus() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_site_sharded_ranks(mode, world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     s = socket.socket()
@@ -71,18 +72,20 @@ def test_site_sharded_two_ranks(mode):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in procs), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    (_, lp0, gr0, lpa0, gra0, ok0, s0, e0, ref), (_, lp1, gr1, lpa1, gra1, ok1, s1, e1, _) = res
-    assert e0 == 0 and e1 == 0 and ok0 and ok1
-    assert np.array_equal(lp0, lp1) and np.array_equal(gr0, gr1), "ranks disagree bitwise"
-    assert np.array_equal(lpa0, lpa1) and np.array_equal(gra0, gra1)
+    _, lp0, gr0, lpa0, gra0, ok0, s0, e0, ref = res[0]
+    assert e0 == 0 and ok0
+    for _, lp1, gr1, lpa1, gra1, ok1, s1, e1, _ in res[1:]:
+        assert e1 == 0 and ok1
+        assert np.array_equal(lp0, lp1) and np.array_equal(gr0, gr1), "ranks disagree bitwise"
+        assert np.array_equal(lpa0, lpa1) and np.array_equal(gra0, gra1)
+        assert np.array_equal(s0, s1), "site-sharded NUTS chains diverged between ranks"
     np.testing.assert_allclose(lp0, ref[0], rtol=2e-6)
     np.testing.assert_allclose(gr0, ref[1], rtol=1e-5, atol=1e-5 * np.abs(ref[1]).max())
     np.testing.assert_allclose(lpa0, ref[0][:5], rtol=2e-6)
-    assert np.array_equal(s0, s1), "site-sharded NUTS chains diverged between ranks"
