@@ -152,3 +152,20 @@ def test_find_heuristic_step_size_option():
     se = np.sqrt(dg.mcse_mean(a) ** 2 + dg.mcse_mean(b) ** 2)
     assert np.all(np.abs(a.reshape(-1, 4).mean(0) - b.reshape(-1, 4).mean(0)) < 5 * se)
     assert np.all(dg.split_gelman_rubin(b) < 1.03)
+
+
+def test_map_init_finds_the_mode_and_fit_accepts_it():
+    import biolith_b200 as bb
+    from biolith_b200.optim import find_map
+
+    data, true = bb.simulate_occupancy("occu", n_site_covs=2, n_obs_covs=1, n_sites=20000,
+                                       deployment_days_per_site=56, random_seed=2)
+    with bb.OccupancyLikelihood("occu", data["site_covs"], data["obs_covs"], data["obs"]) as lk:
+        th, lp, info = find_map(lk)
+        _, g = lk.logp_and_grad(th)
+        # at the mode the gradient is tiny relative to its scale a posterior-sd away (~sqrt(n) = 140)
+        assert np.abs(g).max() < 20.0
+        assert np.allclose(th[:3], true["beta"][0], atol=0.1) and np.allclose(th[3:], true["alpha"][0], atol=0.1)
+    res = bb.fit(bb.models.occu, **data, num_chains=16, num_samples=150, num_warmup=150, init_strategy="map")
+    assert np.all(res.mcmc.summary()["beta"]["r_hat"] < 1.05)
+    assert np.allclose(res.samples["cov_state_1"].mean(), true["beta"][0, 1], atol=0.1)
