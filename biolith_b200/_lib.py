@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbiolith_b200.so")
 
 BL_ABI_VERSION = 1
-BL_MODEL = {"occu": 0, "occu_rn": 1, "occu_cop": 2, "nmixture": 3}
+BL_MODEL = {"occu": 0, "occu_rn": 1, "occu_cop": 2, "nmixture": 3, "occu_cs": 4}
 BL_F32, BL_F64 = 0, 1
 BL_FLAG_FP_CONSTANT, BL_FLAG_FP_UNOCCUPIED, BL_FLAG_PRIOR, BL_FLAG_STRICT_MATH = 1, 2, 4, 8
 

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -34,6 +35,9 @@ cudaError_t launch_occu_rn(const EvalParams& p, int dtype, dim3 grid, size_t sme
 cudaError_t launch_occu_cop(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
 cudaError_t launch_nmixture(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
 cudaError_t launch_nmixture_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
+cudaError_t launch_occu_cs(const EvalParams& p, int dtype, dim3 grid, size_t smem, cudaStream_t stream, int* occ);
+cudaError_t launch_occu_cs_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
+int occu_cs_has_specialisation(int ks, int ko);
 int occu_has_specialisation(int ks, int ko, bool fp);
 cudaError_t launch_occu_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
 cudaError_t launch_occu_rn_summary(const EvalParams& p, int dtype, float* out, cudaStream_t st);
@@ -66,6 +70,7 @@ static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 
     case BL_MODEL_OCCU: return launch_occu(p, ds->desc.dtype, grid, smem, st, occ);
     case BL_MODEL_OCCU_RN: return launch_occu_rn(p, ds->desc.dtype, grid, smem, st, occ);
     case BL_MODEL_NMIXTURE: return launch_nmixture(p, ds->desc.dtype, grid, smem, st, occ);
+    case BL_MODEL_OCCU_CS: return launch_occu_cs(p, ds->desc.dtype, grid, smem, st, occ);
     default: return launch_occu_cop(p, ds->desc.dtype, grid, smem, st, occ);
   }
 }
@@ -110,7 +115,13 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       pl.rn_global = true;
     }
     if (pl.rn_global) extra = 0;  // ... else to (coalesced, L2-resident) global scratch
-    if (!extra) pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit);
+    if (!extra) {
+      // resident blocks per SM the tile ring is sized for: small chain batches are latency-bound (one
+      // tile per warp per iteration), so they trade ring depth for more resident warps
+      int bps = 2;
+      if (const char* ev = getenv("BL_ENGINE_BPS")) bps = atoi(ev) > 0 ? atoi(ev) : bps;
+      pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, bps, ds->smem_limit);
+    }
     pl.rn_scratch_off = (uint32_t)((pl.g.smem_bytes + 127) & ~size_t(127));
     pl.g.smem_bytes = pl.rn_scratch_off + extra;
     const bool want_chain = C >= kChainKernelMinChains && !ds->force_engine;
@@ -281,7 +292,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   if (!d || !out) return fail(BL_ERR_INVALID, "desc/out is NULL");
   *out = nullptr;
   if (d->abi_version != BL_ABI_VERSION) return fail(BL_ERR_INVALID, "ABI version %d != %d", d->abi_version, BL_ABI_VERSION);
-  if (d->model < 0 || d->model > 3) return fail(BL_ERR_INVALID, "unknown model %d", d->model);
+  if (d->model < 0 || d->model > BL_MODEL_OCCU_CS) return fail(BL_ERR_INVALID, "unknown model %d", d->model);
   if ((d->dtype != BL_F32 && d->dtype != BL_F64) || (d->data_dtype != BL_F32 && d->data_dtype != BL_F64))
     return fail(BL_ERR_INVALID, "dtype must be BL_F32 or BL_F64");
   if (d->n_sites < 0 || d->n_periods < 1 || d->n_replicates < 1 || d->n_site_covs < 0 || d->n_obs_covs < 0)
@@ -295,6 +306,10 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
     return fail(BL_ERR_INVALID, "false_positives_constant and false_positives_unoccupied cannot both be True");  // occu.py:112-114
   if (d->model == BL_MODEL_OCCU_RN && fpu) return fail(BL_ERR_INVALID, "occu_rn has no false_positives_unoccupied");
   if (d->model == BL_MODEL_NMIXTURE && (fpc || fpu)) return fail(BL_ERR_INVALID, "nmixture has no false-positive options");
+  if (d->model == BL_MODEL_OCCU_CS && (fpc || fpu)) return fail(BL_ERR_INVALID, "occu_cs has no false-positive options");
+  if (d->model == BL_MODEL_OCCU_CS && (d->flags & BL_FLAG_PRIOR) &&
+      (d->prior_fp_a <= 0 || d->prior_fp_b <= 0 || d->prior_fp_rate <= 0))
+    return fail(BL_ERR_INVALID, "occu_cs priors: Gamma(a, b) of sigma and the Normal scale of mu must be positive");
   if ((d->model == BL_MODEL_OCCU_RN || d->model == BL_MODEL_NMIXTURE) && (d->max_abundance < 1 || d->max_abundance > 1023))
     return fail(BL_ERR_INVALID, "max_abundance must be in [1, 1023]");
   if (d->n_sites > 0 && (!y || !X || !W)) return fail(BL_ERR_INVALID, "y/X/W is NULL");
@@ -307,11 +322,12 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   ds->desc = *d;
   ds->force_engine = (d->flags & BL_FLAG_STRICT_MATH) != 0;
   ds->L = make_layout(d->model, d->n_sites, d->n_periods, d->n_replicates, d->n_site_covs, d->n_obs_covs);
-  ds->n_extras = (fpc ? 1 : 0) + (fpu ? 1 : 0);
+  ds->n_extras = d->model == BL_MODEL_OCCU_CS ? 4 : (fpc ? 1 : 0) + (fpu ? 1 : 0);
   ds->D = d->n_site_covs + 1 + d->n_obs_covs + 1 + ds->n_extras;
   int derived = d->model == BL_MODEL_OCCU ? occu_derived_slots(d->flags)
                 : d->model == BL_MODEL_OCCU_RN ? occu_rn_derived_slots(d->flags)
-                : d->model == BL_MODEL_OCCU_COP ? occu_cop_derived_slots(d->flags) : 0;
+                : d->model == BL_MODEL_OCCU_COP ? occu_cop_derived_slots(d->flags)
+                : d->model == BL_MODEL_OCCU_CS ? 4 : 0;
   ds->DS = ds->D + derived;
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
@@ -435,7 +451,8 @@ int bl_dataset_info(const bl_dataset* ds, bl_info* info) {
   info->n_masked = ds->n_masked;
   info->fields_per_unit = L.F;
   const bool fp = ds->n_extras > 0;
-  info->kernel_variant = ds->desc.model == BL_MODEL_OCCU ? occu_has_specialisation(L.ks, L.ko, fp) : 0;
+  info->kernel_variant = ds->desc.model == BL_MODEL_OCCU ? occu_has_specialisation(L.ks, L.ko, fp)
+                         : ds->desc.model == BL_MODEL_OCCU_CS ? occu_cs_has_specialisation(L.ks, L.ko) : 0;
   return BL_OK;
 }
 
@@ -531,6 +548,7 @@ int bl_site_summary(bl_dataset* ds, const void* theta, int32_t n_draws, float* o
       case BL_MODEL_OCCU: e = launch_occu_summary(p, ds->desc.dtype, d_out, nullptr); break;
       case BL_MODEL_OCCU_RN: e = launch_occu_rn_summary(p, ds->desc.dtype, d_out, nullptr); break;
       case BL_MODEL_NMIXTURE: e = launch_nmixture_summary(p, ds->desc.dtype, d_out, nullptr); break;
+      case BL_MODEL_OCCU_CS: e = launch_occu_cs_summary(p, ds->desc.dtype, d_out, nullptr); break;
       default: e = launch_occu_cop_summary(p, ds->desc.dtype, d_out, nullptr); break;
     }
     if (e != cudaSuccess) { rc = fail(BL_ERR_CUDA, "summary launch: %s", cudaGetErrorString(e)); break; }

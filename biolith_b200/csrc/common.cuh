@@ -34,6 +34,7 @@ constexpr int kMaxStages = 4;
 //                             data constant sum m (y log T - lgamma(y+1)), NW mask words
 //            nmixture:        J floats y (0 if masked), NW mask words, max count, Y0 = sum m y,
 //                             Yw_k = sum_j m y W_jk (Ko floats; data-only parts of the alpha gradient)
+//            occu_cs:         J floats score (0 if masked), NW mask words
 //   every warp-wide read of one field is one coalesced 128-byte (fp32) line, and a whole tile is a
 //   contiguous, 16-byte aligned chunk -> one cp.async.bulk (TMA) per block-tile.
 // ------------------------------------------------------------------------------------------
@@ -63,6 +64,10 @@ inline Layout make_layout(int model, int64_t S, int P, int J, int ks, int ko) {
     L.off_m = f; f += L.nw;
     L.off_sy = f; f += 2 + ko;  // max count, Y0, Yw[ko]
     L.off_t = -1; L.off_n1 = -1;
+  } else if (model == BL_MODEL_OCCU_CS) {
+    L.off_y = f; f += J;
+    L.off_m = f; f += L.nw;
+    L.off_t = -1; L.off_sy = -1; L.off_n1 = -1;
   } else if (model == BL_MODEL_OCCU_COP) {
     L.off_y = f; f += J;
     L.off_t = f; f += J;

@@ -20,6 +20,37 @@ namespace bl {
 // lgamma for small positive arguments used by the prior normaliser (host+device, double)
 __device__ __forceinline__ double log_sigmoid_d(double x) { return fmin(x, 0.0) - log1p(exp(-fabs(x))); }
 
+// occu_cs extras [mu0, x1 = log(mu1 - mu0), log sigma0, log sigma1] (occu_cs.py:146-154): Normal(0, s) on
+// mu0, Normal(0, s) left-truncated at mu0 on mu1 (+ log|J| = x1), Gamma(a, b) on each sigma (+ log|J| = x);
+// s = prior_fp_rate, (a, b) = (prior_fp_a, prior_fp_b) for this model.  which = -1: log-density, 0..3: d/dx_i.
+__device__ inline double cs_prior(const EvalParams& p, const double x[4], int which) {
+  const double s = p.prior_fp_rate, a = p.prior_fp_a, b = p.prior_fp_b;
+  const double h2pi = 0.91893853320467274178, rs2 = 0.70710678118654752440;
+  const double mu0 = x[0], e1 = exp(x[1]), mu1 = mu0 + e1, t = mu0 / s;
+  // log(1 - Phi(t)) and the hazard phi(t) / (1 - Phi(t)), stable for t > 0 through erfcx
+  double log_sf, hazard;
+  if (t > 0.0) {
+    const double ex = erfcx(t * rs2);
+    log_sf = log(0.5 * ex) - 0.5 * t * t;
+    hazard = 0.79788456080286535588 / ex;  // sqrt(2/pi) / erfcx
+  } else {
+    const double sf = 0.5 * erfc(t * rs2);
+    log_sf = log(sf);
+    hazard = exp(-0.5 * t * t - h2pi) / sf;
+  }
+  switch (which) {
+    case -1: {
+      double lp = -0.5 * t * t - log(s) - h2pi;
+      lp += -0.5 * (mu1 / s) * (mu1 / s) - log(s) - h2pi - log_sf + x[1];
+      for (int i = 2; i < 4; ++i) lp += a * log(b) + (a - 1.0) * x[i] - b * exp(x[i]) - lgamma(a) + x[i];
+      return lp;
+    }
+    case 0: return -mu0 / (s * s) - mu1 / (s * s) + hazard / s;
+    case 1: return -mu1 / (s * s) * e1 + 1.0;
+    default: return a - b * exp(x[which]);
+  }
+}
+
 // Adds priors (+ Jacobians) to the raw sums of one chain and writes the outputs.
 template <typename T>
 __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, bool add_const) {
@@ -40,7 +71,12 @@ __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, 
         double z = ((double)theta[KB + i] - p.prior_alpha_loc) / p.prior_alpha_scale;
         lp += -0.5 * z * z - log(p.prior_alpha_scale) - h2pi;
       }
-      for (int i = KB + KA; i < p.D; ++i) {
+      if (p.model == BL_MODEL_OCCU_CS) {
+        const double x[4] = {(double)theta[KB + KA], (double)theta[KB + KA + 1], (double)theta[KB + KA + 2],
+                             (double)theta[KB + KA + 3]};
+        lp += cs_prior(p, x, -1);
+      }
+      for (int i = KB + KA; i < p.D && p.model != BL_MODEL_OCCU_CS; ++i) {
         double x = (double)theta[i];
         if (p.model == BL_MODEL_OCCU_COP) {  // occu_cop: Exponential(rate) on exp(x), + log|J| = x
           lp += log(p.prior_fp_rate) - p.prior_fp_rate * exp(x) + x;
@@ -59,7 +95,11 @@ __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, 
       double x = (double)theta[i];
       if (i < KB) g -= (x - p.prior_beta_loc) / (p.prior_beta_scale * p.prior_beta_scale);
       else if (i < KB + KA) g -= (x - p.prior_alpha_loc) / (p.prior_alpha_scale * p.prior_alpha_scale);
-      else if (p.model == BL_MODEL_OCCU_COP) g += 1.0 - p.prior_fp_rate * exp(x);
+      else if (p.model == BL_MODEL_OCCU_CS) {
+        const double xe[4] = {(double)theta[KB + KA], (double)theta[KB + KA + 1], (double)theta[KB + KA + 2],
+                              (double)theta[KB + KA + 3]};
+        g += cs_prior(p, xe, i - KB - KA);
+      } else if (p.model == BL_MODEL_OCCU_COP) g += 1.0 - p.prior_fp_rate * exp(x);
       else {
         double c1 = 1.0 / (1.0 + exp(-x));
         g += p.prior_fp_a * (1.0 - c1) - p.prior_fp_b * c1;

@@ -64,6 +64,8 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
         y0 += yv;
         for (int k = 0; k < ko; ++k) yw[k] += yv * base[(L.off_w + j * ko + k) * kWarp];
       }
+    } else if (model == BL_MODEL_OCCU_CS) {
+      base[(L.off_y + j) * kWarp] = m ? yv : TO(0);  // any finite score is valid
     } else if (model == BL_MODEL_OCCU_COP) {
       const TO tv = Tdur ? (TO)Tdur[u * J + j] : TO(1);
       if (m && (yv < TO(0) || !isfinite(tv))) atomicOr(err_flag, 2);
@@ -81,7 +83,7 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
     }
     if ((j & 31) == 31 || j == J - 1) {
       base[(L.off_m + (j >> 5)) * kWarp] = word_as<TO>(mw);
-      if (model != BL_MODEL_OCCU_COP && model != BL_MODEL_NMIXTURE)
+      if (model != BL_MODEL_OCCU_COP && model != BL_MODEL_NMIXTURE && model != BL_MODEL_OCCU_CS)
         base[(L.off_y + (j >> 5)) * kWarp] = word_as<TO>(ybits);
       ybits = 0; mw = 0;
     }
@@ -94,7 +96,7 @@ __global__ void pack_kernel(const TI* __restrict__ y, const TI* __restrict__ X, 
     base[L.off_sy * kWarp] = sy;
     base[(L.off_sy + 1) * kWarp] = st;
     base[(L.off_sy + 2) * kWarp] = (TO)cst;
-  } else {
+  } else if (model != BL_MODEL_OCCU_CS) {
     base[L.off_n1 * kWarp] = (TO)n1;
   }
   if (masked) atomicAdd(n_masked, masked);

@@ -115,6 +115,16 @@ def fit(
             if loc is None or scale is None or type(pr).__name__ != "Normal":
                 raise BiolithB200Error(-2, "fit", f"{k}: only Normal(loc, scale) priors are accelerated")
             prior_kw[tgt] = (float(loc), float(scale))
+    if name == "occu_cs":
+        # occu_cs.py:29-30: one distribution or a (f = 0, f = 1) pair; the kernels carry one Normal(0, s) / Gamma(a, b)
+        for k, kind, fields in (("prior_mu", "Normal", ("loc", "scale")), ("prior_sigma", "Gamma", ("concentration", "rate"))):
+            pr = kwargs.get(k)
+            if pr is None:
+                continue
+            if isinstance(pr, tuple) or type(pr).__name__ != kind or (kind == "Normal" and float(pr.loc) != 0.0):
+                raise BiolithB200Error(-2, "fit", f"{k}: only a single zero-centred {kind} prior is accelerated")
+            vals = tuple(float(getattr(pr, f)) for f in fields)
+            prior_kw["prior_mu_scale" if k == "prior_mu" else "prior_sigma"] = vals[1] if k == "prior_mu" else vals
     n_species = kwargs.get("n_species", 1)
     site_names = _covariate_names(site_covs, _as_numpy(site_covs).shape[1])
     obs_np = _as_numpy(obs_covs)
@@ -128,9 +138,9 @@ def fit(
     _, _, obs_np4, _ = ensure_period_dim(None, None, _as_numpy(obs), None)
     n_sp = obs_np4.shape[0]
     n_periods = obs_np4.shape[2]
-    if n_sp > 1 and (fpc or fpu):
-        raise BiolithB200Error(-2, "fit", "n_species > 1 with shared false-positive parameters couples the species "
-                               "and is outside the accelerated path")
+    if n_sp > 1 and (fpc or fpu or name == "occu_cs"):
+        raise BiolithB200Error(-2, "fit", "n_species > 1 with shared false-positive / score parameters couples the "
+                               "species and is outside the accelerated path")
     parts = []
     for sp in range(n_sp):
         # species are independent problems sharing the covariates (one handle each, occu.py:182-186)
@@ -187,7 +197,12 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs,
         "alpha": th[:, :, None, Ks + 1 : Ks + Ko + 2],
     }
     i = Ks + Ko + 2
-    if name == "occu_cop":
+    if name == "occu_cs":  # occu_cs.py:148-154; mu1 = mu0 + exp(x) (left-truncated at mu0)
+        grouped["mu0"] = th[:, :, i]
+        grouped["mu1"] = th[:, :, i] + np.exp(th[:, :, i + 1])
+        grouped["sigma0"] = np.exp(th[:, :, i + 2])
+        grouped["sigma1"] = np.exp(th[:, :, i + 3])
+    elif name == "occu_cop":
         if fpc:
             grouped["rate_fp_constant"] = np.exp(th[:, :, i]); i += 1
         if fpu:

@@ -44,7 +44,7 @@ def ensure_period_dim(site_covs, obs_covs, obs, session_duration=None):
 
 
 class OccupancyLikelihood:
-    """Packed dataset resident in HBM + the fused logp/grad kernels for one of the three models."""
+    """Packed dataset resident in HBM + the fused logp/grad kernels for one of the accelerated models."""
 
     def __init__(
         self,
@@ -64,6 +64,8 @@ class OccupancyLikelihood:
         prior_alpha: Tuple[float, float] = (0.0, 1.0),
         prior_fp_beta: Tuple[float, float] = (2.0, 5.0),
         prior_fp_rate: float = 1.0,
+        prior_mu_scale: float = 10.0,
+        prior_sigma: Tuple[float, float] = (5.0, 1.0),
         device: int = 0,
         max_chains: int = 0,
     ):
@@ -96,6 +98,10 @@ class OccupancyLikelihood:
             session_duration = None
         if session_duration is not None and session_duration.shape != (S, P, J):
             raise ValueError("session_duration must have shape (n_sites, n_periods, n_replicates)")
+        if model == "occu_cs":
+            # occu_cs.py:29-30: Normal(0, s) on mu0 / mu1 and Gamma(a, b) on sigma0 / sigma1 travel in the
+            # prior_fp_* slots of bl_desc (include/biolith_b200.h)
+            prior_fp_beta, prior_fp_rate = tuple(prior_sigma), float(prior_mu_scale)
         code, npdt = _DT[dtype]
         # the reference casts to the compute dtype on ingestion (jnp.array, data.py:135-140)
         data_dt = np.float64 if any(a.dtype == np.float64 for a in (site_covs, obs_covs, obs)) else np.float32

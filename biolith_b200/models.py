@@ -30,7 +30,9 @@ occu_cop = _Model("occu_cop", "Count-detection occupancy (Pautrel et al. 2024); 
 
 nmixture = _Model("nmixture", "N-mixture model for repeated counts (Royle 2004); biolith/models/nmixture.py:19-220")
 
-SUPPORTED = {"occu": occu, "occu_rn": occu_rn, "occu_cop": occu_cop, "nmixture": nmixture}
+occu_cs = _Model("occu_cs", "Continuous-score occupancy (Rhinehart et al. 2022); biolith/models/occu_cs.py:18-223")
+
+SUPPORTED = {"occu": occu, "occu_rn": occu_rn, "occu_cop": occu_cop, "nmixture": nmixture, "occu_cs": occu_cs}
 
 # keyword arguments of the reference models that the accelerated path honours / must reject
 HONOURED = {"false_positives_constant", "false_positives_unoccupied", "max_abundance", "n_species"}

@@ -34,6 +34,7 @@ Reference lines restated (paths relative to /root/reference):
   biolith/models/occu_rn.py:123-222   (occu_rn body)
   biolith/models/occu_cop.py:146-255  (occu_cop body)
   biolith/models/nmixture.py:124-220  (nmixture body)
+  biolith/models/occu_cs.py:120-223   (occu_cs body)
   biolith/regression/linear.py:16-66  (LinearRegression)
   biolith/utils/modeling.py:8-39      (mask_missing_obs / flatten / reshape)
   biolith/utils/distributions.py:6-40 (RightTruncatedPoisson)
@@ -47,6 +48,11 @@ numpyro>=0.18; recalled, not vendored):
   BinomialProbs.log_prob    = gammaln(n+1) - gammaln(v+1) - gammaln(n-v+1) + xlogy(v, p) + xlog1py(n-v, -p)
   CategoricalLogits         = logits - logsumexp(logits)   (normalised)
   MaskedDistribution        = where(m, base.log_prob(where(m, v, feasible)), 0)
+  Normal.log_prob           = -((v - loc)^2) / (2 scale^2) - log(scale) - log(sqrt(2 pi))
+  TruncatedDistribution(Normal(loc, s), low=a).log_prob(v) = Normal.log_prob(v) - log(1 - Phi((a - loc)/s));
+                              support greater_than(a) -> biject_to = Exp then Affine(a, 1): v = a + exp(x)
+                              (dynamic support: the transform is rebuilt from the traced `low` every call)
+  Gamma(c, r).log_prob      = c log r + (c-1) log v - r v - gammaln(c);  positive support -> ExpTransform
   Beta / Exponential priors are sampled in unconstrained space through
   SigmoidTransform / ExpTransform with their log-Jacobians (potential_fn).
 
@@ -56,6 +62,7 @@ Parameter vector layout used everywhere in this repo (one chain):
      occu     : logit(prob_fp_constant), logit(prob_fp_unoccupied)
      occu_rn  : logit(prob_fp_constant)
      occu_cop : log(rate_fp_constant), log(rate_fp_unoccupied)
+     occu_cs  : mu0, log(mu1 - mu0), log(sigma0), log(sigma1)   (always present)
 Only n_species == 1 is restated in closed form (the enumerated form handles Sp >= 1).
 """
 
@@ -65,7 +72,7 @@ from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
-from scipy.special import expit, gammaln, xlog1py, xlogy
+from scipy.special import expit, gammaln, log_ndtr, xlog1py, xlogy
 
 LOG_2PI = float(np.log(2.0 * np.pi))
 
@@ -137,6 +144,8 @@ def prepare(site_covs, obs_covs, obs, session_duration=None, dtype=np.float32) -
 
 
 def n_extras(model: str, fp_constant=False, fp_unoccupied=False) -> int:
+    if model == "occu_cs":
+        return 4
     if model == "occu_rn":
         assert not fp_unoccupied
     return int(bool(fp_constant)) + int(bool(fp_unoccupied))
@@ -379,6 +388,66 @@ def nmixture_log_joint_enumerated(theta, site_covs, obs_covs, obs, *, max_abunda
         site_ll = ll.sum(axis=1, keepdims=True) + log_pN
     site_ll = np.where(np.isnan(site_ll), -np.inf, site_ll)
     return float(lp + logsumexp(site_ll, axis=0).sum() + factor.sum())
+
+
+def _cs_extras(x, prior, prior_mu_scale, prior_sigma):
+    """occu_cs.py:146-154 in unconstrained space: x = [mu0, log(mu1 - mu0), log sigma0, log sigma1].
+
+    Returns (mu0, mu1, sigma0, sigma1), the log-prior incl. log-Jacobians, and d(log-prior)/dx holding the
+    CONSTRAINED values fixed for the likelihood part (the caller chains the likelihood gradient)."""
+    mu0, x1, xs0, xs1 = (float(v) for v in x)
+    s = float(prior_mu_scale)
+    a, b = (float(v) for v in prior_sigma)
+    e1 = np.exp(x1)
+    mu1 = mu0 + e1
+    sg0, sg1 = np.exp(xs0), np.exp(xs1)
+    lp = 0.0
+    g = np.zeros(4)
+    if prior:
+        t = mu0 / s
+        lp += normal_log_prob(mu0, 0.0, s)
+        lp += normal_log_prob(mu1, 0.0, s) - log_ndtr(-t) + x1  # left-truncated at mu0, + log|d mu1/dx1|
+        hazard = np.exp(-0.5 * t * t - 0.5 * LOG_2PI - log_ndtr(-t))  # phi(t) / (1 - Phi(t))
+        g[0] = -mu0 / s**2 - mu1 / s**2 + hazard / s
+        g[1] = -mu1 / s**2 * e1 + 1.0
+        for i, (xs, sg) in enumerate(((xs0, sg0), (xs1, sg1))):
+            lp += a * np.log(b) + (a - 1.0) * xs - b * sg - gammaln(a) + xs
+            g[2 + i] = a - b * sg
+    return (mu0, mu1, sg0, sg1), lp, g
+
+
+def occu_cs_log_joint_enumerated(theta, site_covs, obs_covs, obs, *, dtype=np.float32, prior=True,
+                                 prior_mu_scale=10.0, prior_sigma=(5.0, 1.0)):
+    """occu_cs.py:120-223 op by op (continuous-score occupancy, Rhinehart et al. 2022): two enumerated
+    latents, z per (period, site) and f per visit; theta = [beta(Sp*Kb) | alpha(Sp*Ka) | mu0, x1, xs0, xs1]."""
+    finfo = _finfo(dtype)
+    pr = prepare(site_covs, obs_covs, obs, dtype=dtype)
+    Sp, S, P, J = pr.y.shape
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    theta = np.asarray(theta, np.float64)
+    nb, na = Sp * (Ks + 1), Sp * (Ko + 1)
+    beta = theta[:nb].reshape(Sp, Ks + 1)
+    alpha = theta[nb : nb + na].reshape(Sp, Ko + 1)
+    assert theta.size == nb + na + 4
+    (mu0, mu1, sg0, sg1), lp, _ = _cs_extras(theta[nb + na :], prior, prior_mu_scale, prior_sigma)
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+    site_flat, site_shape = _flatten(pr.X.transpose(1, 0))
+    obs_flat, obs_shape = _flatten(pr.W.transpose(3, 2, 1, 0))
+    y = pr.y.transpose(3, 2, 1, 0)  # (J,P,S,Sp)
+    m = np.isfinite(y)
+    psi = np.broadcast_to(expit(_linear(beta, site_flat).reshape(site_shape + (Sp,))), (P, S, Sp))
+    z = np.array([0.0, 1.0]).reshape(1, 2, 1, 1, 1, 1)  # enum dim of z
+    f = np.array([0.0, 1.0]).reshape(2, 1, 1, 1, 1, 1)  # enum dim of f (allocated after z)
+    log_pz = bernoulli_log_prob(psi, z, finfo)  # (1,2,1,P,S,Sp)
+    p = expit(_linear(alpha, obs_flat).reshape(obs_shape + (Sp,)))  # (J,P,S,Sp)
+    log_pf = bernoulli_log_prob(z * p, f, finfo)  # (2,2,J,P,S,Sp), occu_cs.py:202-213
+    v = np.where(m, y, 0.0)
+    ll = normal_log_prob(v, (1 - f) * mu0 + f * mu1, (1 - f) * sg0 + f * sg1)  # occu_cs.py:215-223
+    ll = np.where(m, ll, 0.0)
+    visit = logsumexp(log_pf + ll, axis=0)  # sum out f inside the replicate plate -> (2,J,P,S,Sp)
+    site_ll = visit.sum(axis=1, keepdims=True) + log_pz[0]  # (2,1,P,S,Sp)
+    return float(lp + logsumexp(site_ll, axis=0).sum())
 
 
 # ==================================================================== closed form
@@ -657,11 +726,68 @@ def nmixture_logp_grad(theta, pr: Prepared, *, max_abundance=100, dtype=np.float
     return logp, grad
 
 
+def occu_cs_logp_grad(theta, pr: Prepared, *, dtype=np.float32, prior=True, prior_mu_scale=10.0,
+                      prior_sigma=(5.0, 1.0), return_site_terms=False):
+    """Closed-form occu_cs log-density + gradient.  Per visit, with n0/n1 the two Normal log-densities of
+    the score and q the clamped Bernoulli probability of f = 1 in the branch (z = 1: p~_j, z = 0: tiny):
+       L_j = logaddexp(log(1-q) + n0_j, log q + n1_j),  w_j = P(f_j = 1 | s_j, z)
+       l = logaddexp(log psi~ + sum_j m_j L_j(1), log(1-psi~) + sum_j m_j L_j(0)),  r = P(z = 1 | s)
+       dL_j/dnu = w_j - p_j (z = 1, in range), dL_j/dmu_f = w_f e_f / sigma_f, dL_j/dlog sigma_f = w_f (e_f^2 - 1)."""
+    finfo = _finfo(dtype)
+    X, W, T, y, m = _units(pr)
+    Ks, Ko = X.shape[1], W.shape[2]
+    theta = np.asarray(theta, np.float64)
+    assert theta.size == Ks + Ko + 6
+    beta, alpha = theta[: Ks + 1], theta[Ks + 1 : Ks + Ko + 2]
+    (mu0, mu1, sg0, sg1), lp, g_prior = _cs_extras(theta[Ks + Ko + 2 :], prior, prior_mu_scale, prior_sigma)
+    eta = beta[0] + X @ beta[1:]
+    nu = alpha[0] + W @ alpha[1:]
+    psi, logpsi, log1mpsi, in_psi = _clamped_log_sigmoid_pair(eta, finfo)
+    p, logq, log1mq, in_p = _clamped_log_sigmoid_pair(nu, finfo)
+    e0, e1 = (y - mu0) / sg0, (y - mu1) / sg1
+    n0 = -0.5 * e0 * e0 - np.log(sg0) - 0.5 * LOG_2PI
+    n1 = -0.5 * e1 * e1 - np.log(sg1) - 0.5 * LOG_2PI
+    mf = m.astype(np.float64)
+
+    def branch(lq, l1q):
+        a0, a1 = l1q + n0, lq + n1
+        L = np.logaddexp(a0, a1)
+        w1 = expit(a1 - a0)
+        return (mf * L).sum(axis=1), mf * w1
+
+    L1, w1 = branch(logq, log1mq)
+    L0, v1 = branch(np.full_like(nu, np.log(finfo.tiny)), np.full_like(nu, np.log1p(-finfo.tiny)))
+    a = logpsi + L1
+    b = log1mpsi + L0
+    ell = np.logaddexp(a, b)
+    r = expit(a - b)
+    d_eta = np.where(in_psi, r - psi, 0.0)
+    d_nu = r[:, None] * np.where(in_p, w1 - mf * p, 0.0)
+    g_beta = np.concatenate([[d_eta.sum()], X.T @ d_eta])
+    g_alpha = np.concatenate([[d_nu.sum()], np.einsum("uj,ujk->k", d_nu, W)])
+    wf1 = r[:, None] * w1 + (1 - r)[:, None] * v1            # P(f = 1 | s), mixed over z
+    wf0 = mf - wf1
+    g_mu0 = (wf0 * e0).sum() / sg0
+    g_mu1 = (wf1 * e1).sum() / sg1
+    g_xs0 = (wf0 * (e0 * e0 - 1.0)).sum()
+    g_xs1 = (wf1 * (e1 * e1 - 1.0)).sum()
+    g_ext = np.array([g_mu0 + g_mu1, g_mu1 * (mu1 - mu0), g_xs0, g_xs1]) + g_prior  # mu1 = mu0 + exp(x1)
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+        g_beta = g_beta - beta
+        g_alpha = g_alpha - alpha
+    logp = float(lp + ell.sum())
+    grad = np.concatenate([g_beta, g_alpha, g_ext]).astype(np.float64)
+    if return_site_terms:
+        return logp, grad, dict(ell=ell, r=r, psi=psi, eta=eta, nu=nu)
+    return logp, grad
+
+
 # ------------------------------------------------------------------ conveniences
 def logp_grad(model: str, theta, pr: Prepared, **kw):
     """Dispatch on model name; theta (D,) or (C, D) -> (logp[C], grad[C,D])."""
     fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad,
-          "nmixture": nmixture_logp_grad}[model]
+          "nmixture": nmixture_logp_grad, "occu_cs": occu_cs_logp_grad}[model]
     theta = np.asarray(theta, np.float64)
     if theta.ndim == 1:
         return fn(theta, pr, **kw)
@@ -675,6 +801,7 @@ def log_joint_enumerated(model: str, theta, data: dict, **kw):
         "occu_rn": occu_rn_log_joint_enumerated,
         "occu_cop": occu_cop_log_joint_enumerated,
         "nmixture": nmixture_log_joint_enumerated,
+        "occu_cs": occu_cs_log_joint_enumerated,
     }[model]
     args = [data["site_covs"], data["obs_covs"], data["obs"]]
     if model == "occu_cop":
@@ -704,7 +831,7 @@ def expected_mask(site_covs, obs_covs, obs) -> np.ndarray:
 def site_summary(model: str, thetas, pr: Prepared, **kw):
     """Per-unit posterior summaries over draws (checker for bl_site_summary): arrays of length S*P."""
     fn = {"occu": occu_logp_grad, "occu_rn": occu_rn_logp_grad, "occu_cop": occu_cop_logp_grad,
-          "nmixture": nmixture_logp_grad}[model]
+          "nmixture": nmixture_logp_grad, "occu_cs": occu_cs_logp_grad}[model]
     ells, a1, a2 = [], [], []
     for th in np.asarray(thetas, np.float64):
         _, _, t = fn(th, pr, prior=False, return_site_terms=True, **kw)

@@ -13,6 +13,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = [
     "occu_default", "occu_missing", "occu_5x3", "occu_fp_const", "occu_fp_unocc",
     "rn_default", "rn_5x3", "cop_default", "cop_missing_5x3", "cop_both_fp", "nmix_default", "nmix_missing_5x3",
+    "cs_default", "cs_missing_5x3",
 ]
 
 

@@ -49,7 +49,9 @@ def build(name, model, data, true, model_kw, sim_kw):
     fpc = bool(model_kw.get("fp_constant", False))
     fpu = bool(model_kw.get("fp_unoccupied", False))
     extras = []
-    if model == "occu_cop":
+    if model == "occu_cs":  # [mu0, log(mu1 - mu0), log sigma0, log sigma1] at the simulator's truth
+        extras = [true["mu0"], np.log(true["mu1"] - true["mu0"]), np.log(true["sigma0"]), np.log(true["sigma1"])]
+    elif model == "occu_cop":
         extras = ([np.log(0.1)] if fpc else []) + ([np.log(0.1)] if fpu else [])
     else:
         extras = ([-2.0] if fpc else []) + ([-2.0] if fpu else [])
@@ -109,10 +111,15 @@ def main():
         ("nmix_missing_5x3", "nmixture", m.simulate_nmixture,
          dict(n_site_covs=5, n_obs_covs=3, n_sites=150, deployment_days_per_site=70, simulate_missing=True),
          dict(max_abundance=60)),
+        ("cs_default", "occu_cs", m.simulate_cs, dict(), dict()),
+        ("cs_missing_5x3", "occu_cs", m.simulate_cs,
+         dict(n_site_covs=5, n_obs_covs=3, n_sites=150, deployment_days_per_site=70, simulate_missing=True), dict()),
         ("cop_both_fp", "occu_cop", m.simulate_cop,
          dict(n_site_covs=1, n_obs_covs=2, n_sites=80, deployment_days_per_site=70),
          dict(fp_constant=True, fp_unoccupied=True)),
     ]
+    only = sys.argv[1:]  # optional name prefixes: rebuild just those fixtures
+    jobs = [j for j in jobs if not only or any(j[0].startswith(o) for o in only)]
     sims = [(name, model, sim(**sim_kw), sim_kw, model_kw) for name, model, sim, sim_kw, model_kw in jobs]
     remove_stubs()
     for name, model, (data, true), sim_kw, model_kw in sims:

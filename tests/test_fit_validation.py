@@ -42,7 +42,7 @@ def test_unknown_model_and_regressor_raise():
 def test_model_descriptors_mirror_reference_names():
     import biolith_b200 as bb
 
-    assert set(bb.models.SUPPORTED) == {"occu", "occu_rn", "occu_cop", "nmixture"}
+    assert set(bb.models.SUPPORTED) == {"occu", "occu_rn", "occu_cop", "nmixture", "occu_cs"}
     assert bb.models.occu.__name__ == "occu"
     with pytest.raises(RuntimeError):
         bb.models.occu()

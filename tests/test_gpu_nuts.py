@@ -169,3 +169,23 @@ def test_map_init_finds_the_mode_and_fit_accepts_it():
     res = bb.fit(bb.models.occu, **data, num_chains=16, num_samples=150, num_warmup=150, init_strategy="map")
     assert np.all(res.mcmc.summary()["beta"]["r_hat"] < 1.05)
     assert np.allclose(res.samples["cov_state_1"].mean(), true["beta"][0, 1], atol=0.1)
+
+
+def test_fit_occu_cs_recovers_truth():
+    """The reference's own acceptance test, biolith/models/occu_cs.py:365-392 (simulate_cs with missing
+    data; psi atol 0.1, coefficients atol 0.5, score means / scales atol 1)."""
+    import biolith_b200 as bb
+
+    data, true = bb.simulate_occupancy("occu_cs", simulate_missing=True, random_seed=0)
+    res = bb.fit(bb.models.occu_cs, **data, num_chains=8, num_samples=300, num_warmup=300, timeout=600)
+    assert np.allclose(res.samples["psi"].mean(), true["z"].mean(), atol=0.1)
+    for i in range(2):
+        assert np.allclose(res.samples[f"cov_state_{i}"].mean(), true["beta"][0, i], atol=0.5)
+        assert np.allclose(res.samples[f"cov_det_{i}"].mean(), true["alpha"][0, i], atol=0.5)
+    for k in ("mu0", "mu1", "sigma0", "sigma1"):
+        assert np.allclose(res.samples[k].mean(), true[k], atol=1), k
+    assert np.all(res.samples["mu1"] > res.samples["mu0"])  # the truncation is a hard constraint
+    s = res.mcmc.summary()
+    assert np.all(s["beta"]["r_hat"] < 1.05) and np.all(s["sigma1"]["r_hat"] < 1.05)
+    ss = res.mcmc.info["site_summary"]
+    assert np.corrcoef(ss["occupancy_prob"][:, 0], true["z"][0, 0, :])[0, 1] > 0.9

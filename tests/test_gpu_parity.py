@@ -11,7 +11,7 @@ from conftest import GOLDEN_NAMES, load_golden
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = {"occu", "occu_rn", "occu_cop", "nmixture"}
+IMPLEMENTED = {"occu", "occu_rn", "occu_cop", "nmixture", "occu_cs"}
 RTOL = {"float32": 1e-5, "float64": 1e-10}
 
 
@@ -80,7 +80,7 @@ def test_chain_batching_is_consistent(n_chains):
 
 @pytest.mark.parametrize("S,P,J,ks,ko", [(1, 1, 1, 1, 1), (33, 1, 5, 2, 1), (257, 1, 8, 5, 3), (40, 3, 4, 3, 2),
                                          (1000, 1, 40, 1, 1), (64, 2, 33, 7, 9), (50, 1, 6, 0, 0)])
-@pytest.mark.parametrize("model", ["occu", "occu_rn", "occu_cop", "nmixture"])
+@pytest.mark.parametrize("model", ["occu", "occu_rn", "occu_cop", "nmixture", "occu_cs"])
 def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
     import biolith_b200 as bb
     from oracle import occupancy as orc
@@ -94,6 +94,9 @@ def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
         y = rng.poisson(2.0, size=(1, S, P, J)).astype(float)
     elif model == "nmixture":
         y = rng.binomial(rng.poisson(3.0, size=(1, S, P, 1)), 0.4, size=(1, S, P, J)).astype(float)
+    elif model == "occu_cs":
+        y = np.where(rng.uniform(size=(1, S, P, J)) < 0.3, rng.normal(10, 5, size=(1, S, P, J)),
+                     rng.normal(0, 10, size=(1, S, P, J)))
     else:
         y = (rng.uniform(size=(1, S, P, J)) < 0.35).astype(float)
     # ragged visits: trailing replicates missing, plus NaNs in covariates
@@ -106,8 +109,10 @@ def test_ragged_shapes_against_oracle(model, S, P, J, ks, ko):
     T = rng.uniform(0.5, 9.0, size=(S, P, J)) if model == "occu_cop" else None
     kw = dict(fp_constant=True) if model == "occu_cop" else (
         dict(max_abundance=30) if model in ("occu_rn", "nmixture") else {})
-    D = ks + ko + 2 + (1 if model == "occu_cop" else 0)
+    D = ks + ko + 2 + (1 if model == "occu_cop" else 4 if model == "occu_cs" else 0)
     th = rng.uniform(-1.5, 1.5, size=(6, D))
+    if model == "occu_cs":
+        th[0, -4:] = [0.3, np.log(9.0), np.log(11.0), np.log(4.0)]  # near the generating score distributions
     pr = orc.prepare(X, W, y, T)
     ref_lp, ref_gr = orc.logp_grad(model, th, pr, **kw)
     with bb.OccupancyLikelihood(model, X, W, y, T, false_positives_constant=(model == "occu_cop"),
@@ -207,7 +212,7 @@ def test_config2_full_size_against_c_oracle():
 
 
 @pytest.mark.parametrize("name", ["occu_5x3", "occu_missing", "rn_5x3", "cop_missing_5x3", "nmix_missing_5x3",
-                                  "nmix_default"])
+                                  "nmix_default", "cs_missing_5x3", "cs_default"])
 def test_strict_math_flag(name):
     """BL_FLAG_STRICT_MATH (libm expf/log1pf/IEEE division) and the default bounded-error SFU forms
     both meet the fp32 tolerance; their mutual difference is at fp32-rounding level."""
@@ -283,7 +288,7 @@ def test_cop_chain_kernel_against_oracle(ks, ko, fpc, fpu):
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
 @pytest.mark.parametrize("name", ["occu_missing", "occu_fp_const", "rn_5x3", "cop_missing_5x3", "cop_both_fp",
-                                  "nmix_missing_5x3"])
+                                  "nmix_missing_5x3", "cs_missing_5x3"])
 def test_site_summary_streaming_kernel(name, dtype):
     """bl_site_summary (psi / occupancy probability / pointwise lppd and p_waic per unit, streamed over
     draws) against the oracle's per-site terms."""

@@ -9,7 +9,7 @@ from biolith_b200.simulate import simulate_occupancy
 
 @pytest.mark.parametrize("name", ["occu_default", "occu_missing", "occu_5x3", "occu_fp_const", "occu_fp_unocc",
                                   "rn_default", "rn_5x3", "cop_default", "cop_missing_5x3", "cop_both_fp",
-                                  "nmix_default", "nmix_missing_5x3"])
+                                  "nmix_default", "nmix_missing_5x3", "cs_default", "cs_missing_5x3"])
 def test_generator_matches_reference_fixture(name):
     from conftest import load_golden
 
