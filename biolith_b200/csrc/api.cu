@@ -49,20 +49,23 @@ size_t occu_rn_extra_smem(const Layout& L, int K, int elem);
 bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 size_t occu_chain_smem(const Layout& L, int nstage, int block_threads);
-int occu_chain_block_threads(int ks, int ko);
+int occu_chain_block_threads(int ks, int ko, int C);
 bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags);
-int occu_rn_chain_block_threads();
-size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D);
+int occu_rn_chain_block_threads(int C);
+size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D, int bt);
 cudaError_t launch_occu_rn_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 bool occu_cop_chain_supported(int dtype, int ks, int ko, uint32_t flags);
-int occu_cop_chain_block_threads();
-size_t occu_cop_chain_smem(const Layout& L, int nstage);
+int occu_cop_chain_block_threads(int C);
+size_t occu_cop_chain_smem(const Layout& L, int nstage, int bt);
 cudaError_t launch_occu_cop_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
 
-constexpr int kChainKernelMinChains = 128;  // below this a 256-thread chain block is mostly idle lanes
+// smallest batch handed to the lane = chain kernels: their 128-thread blocks (idle warps skip the arithmetic)
+// overtake the site-parallel engine at 32 chains for all three models (B200, ms per evaluation, chain /
+// engine: occu 0.47 / 0.54, occu_rn 9.1 / 14.7, occu_cop 0.36 / 0.45); at 16 chains the engine wins.
+constexpr int kChainKernelMinChains = 32;
 
 static cudaError_t launch_model(const bl_dataset* ds, const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st,
                                 int* occ) {
@@ -95,6 +98,8 @@ static void fill_params(const bl_dataset* ds, EvalParams& p) {
   p.prior_fp_a = ds->desc.prior_fp_a;
   p.prior_fp_b = ds->desc.prior_fp_b;
   p.prior_fp_rate = ds->desc.prior_fp_rate;
+  p.nch = 4;
+  if (const char* ev = getenv("BL_ENGINE_NCH")) p.nch = atoi(ev);
 }
 
 // geometry for C chains (cached); grows the fp64 partial workspace when needed
@@ -120,26 +125,32 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       // tile per warp per iteration), so they trade ring depth for more resident warps
       int bps = 2;
       if (const char* ev = getenv("BL_ENGINE_BPS")) bps = atoi(ev) > 0 ? atoi(ev) : bps;
-      pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, bps, ds->smem_limit);
+      int wc = 0;  // A/B switch: "old" = the previous rule (as many chain-groups as chains, up to 8)
+      if (const char* ev = getenv("BL_ENGINE_WC"))
+        wc = !strcmp(ev, "old") ? pow2_floor(C < kWarpsPerBlock ? (C < 1 ? 1 : C) : kWarpsPerBlock) : atoi(ev);
+      pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, bps, ds->smem_limit, wc);
     }
     pl.rn_scratch_off = (uint32_t)((pl.g.smem_bytes + 127) & ~size_t(127));
     pl.g.smem_bytes = pl.rn_scratch_off + extra;
-    const bool want_chain = C >= kChainKernelMinChains && !ds->force_engine;
+    int chain_min = kChainKernelMinChains;
+    if (const char* ev = getenv("BL_CHAIN_MIN")) chain_min = atoi(ev) > 0 ? atoi(ev) : chain_min;
+    const bool want_chain = C >= chain_min && !ds->force_engine;
     pl.chain_kernel = 0;
     if (want_chain && ds->desc.model == BL_MODEL_OCCU &&
         occu_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
       pl.chain_kernel = 1;
     if (want_chain && ds->desc.model == BL_MODEL_OCCU_RN &&
         occu_rn_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags) &&
-        occu_rn_chain_smem(ds->L, 2, ds->desc.max_abundance, ds->D) <= ds->smem_limit)
+        occu_rn_chain_smem(ds->L, 2, ds->desc.max_abundance, ds->D, occu_rn_chain_block_threads(C)) <= ds->smem_limit)
       pl.chain_kernel = 2;
     if (want_chain && ds->desc.model == BL_MODEL_OCCU_COP &&
         occu_cop_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
       pl.chain_kernel = 3;
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
-      const int bt = pl.chain_kernel == 1   ? occu_chain_block_threads(ds->L.ks, ds->L.ko)
-                     : pl.chain_kernel == 2 ? occu_rn_chain_block_threads()
-                                            : occu_cop_chain_block_threads();  // chains per block
+      const int bt = pl.chain_kernel == 1   ? occu_chain_block_threads(ds->L.ks, ds->L.ko, C)
+                     : pl.chain_kernel == 2 ? occu_rn_chain_block_threads(C)
+                                            : occu_cop_chain_block_threads(C);  // chains per block
+      pl.chain_bt = bt;
       pl.g.n_chunks = (C + bt - 1) / bt;
       pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
       pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
@@ -148,12 +159,12 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       if (pl.chain_kernel == 1) {
         pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage, bt);
       } else if (pl.chain_kernel == 3) {
-        pl.g.smem_bytes = occu_cop_chain_smem(ds->L, pl.g.nstage);
+        pl.g.smem_bytes = occu_cop_chain_smem(ds->L, pl.g.nstage, bt);
       } else {
         while (pl.g.nstage > 2 &&
-               occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D) > ds->smem_limit)
+               occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D, bt) > ds->smem_limit)
           --pl.g.nstage;
-        pl.g.smem_bytes = occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D);
+        pl.g.smem_bytes = occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D, bt);
         pl.rn_global = false;
       }
     }
@@ -162,6 +173,7 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
                   ds->smem_limit);
     EvalParams p;
     fill_params(ds, p);
+    p.chain_bt = pl.chain_bt;
     int occ = 0;
     cudaError_t e = pl.chain_kernel == 1   ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 2 ? launch_occu_rn_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
@@ -234,6 +246,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.WC = pl->g.WC;
   p.WS = pl->g.WS;
   p.nstage = pl->g.nstage;
+  p.chain_bt = pl->chain_bt;
   p.nsplit = pl->g.nsplit;
   p.n_block_tiles = pl->g.n_block_tiles;
   p.rn_scratch_off = pl->rn_scratch_off;

@@ -47,7 +47,8 @@ __device__ inline double cs_prior(const EvalParams& p, const double x[4], int wh
     }
     case 0: return -mu0 / (s * s) - mu1 / (s * s) + hazard / s;
     case 1: return -mu1 / (s * s) * e1 + 1.0;
-    default: return a - b * exp(x[which]);
+    case 2: return a - b * exp(x[2]);
+    default: return a - b * exp(x[3]);
   }
 }
 
@@ -142,6 +143,25 @@ __device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int nc
   if (tid == 0) p.counters[blockIdx.y] = 0;  // self-reset for the next launch
 }
 
+// Sums q[0..NQ) of one (warp-tile, chain) over the 32 lanes into the warp's fp64 accumulator row, in
+// chunks of <= 32 quantities through the transposed butterfly (fixed order -> deterministic).
+template <typename T, int OFF, int NQM>
+__device__ __forceinline__ void reduce_into(const T* __restrict__ q, bool valid, int lane, int NQ,
+                                            double* __restrict__ acc) {
+  if constexpr (OFF < NQM) {
+    constexpr int REM = NQM - OFF;
+    constexpr int P = REM >= 32 ? 32 : (REM > 16 ? 32 : REM > 8 ? 16 : REM > 4 ? 8 : REM > 2 ? 4 : REM > 1 ? 2 : 1);
+    constexpr int SH = 5 - Log2<P>::v;
+    T v[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) v[i] = (valid && OFF + i < NQ) ? q[OFF + i < NQM ? OFF + i : 0] : T(0);
+    const T r = transpose_reduce<T, P>(v, lane);
+    const int idx = OFF + (lane >> SH);
+    if ((lane & ((1 << SH) - 1)) == 0 && idx < NQ) acc[idx] += (double)r;
+    reduce_into<T, OFF + 32, NQM>(q, valid, lane, NQ, acc);
+  }
+}
+
 template <typename T, class Model, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -200,24 +220,33 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalPar
     typename Model::Site site;
     Model::load_site(p, tile, lane, site);
 
-    for (int ci = wc; ci < ncb; ci += WC) {
-      T q[Model::kNQMax];
-      Model::site_chain(p, tile, lane, site, s_theta + (size_t)ci * DS, q);
-      double* acc = s_acc + ((size_t)ws * p.CB + ci) * NQ;
-      if constexpr (Model::kNQMax <= 32) {
-        T mine = T(0);
+    int ci = wc;
+    if constexpr (Model::kMultiChain >= 4) {
+      if (p.nch >= 4) {
+        for (; ci + 3 * WC < ncb; ci += 4 * WC) {
+          T q4[4][Model::kNQMax];
+          Model::template site_chain_n<4>(p, tile, lane, site, s_theta + (size_t)ci * DS, WC * DS, q4);
 #pragma unroll
-        for (int i = 0; i < Model::kNQMax; ++i) {
-          T v = warp_sum(valid ? q[i] : T(0));
-          if (lane == i) mine = v;
-        }
-        if (lane < NQ) acc[lane] += (double)mine;
-      } else {
-        for (int i = 0; i < NQ; ++i) {
-          T v = warp_sum(valid ? q[i] : T(0));
-          if (lane == 0) acc[i] += (double)v;
+          for (int c = 0; c < 4; ++c)
+            reduce_into<T, 0, Model::kNQMax>(q4[c], valid, lane, NQ, s_acc + ((size_t)ws * p.CB + ci + c * WC) * NQ);
         }
       }
+    }
+    if constexpr (Model::kMultiChain >= 2) {
+      if (p.nch >= 2) {
+        for (; ci + WC < ncb; ci += 2 * WC) {
+          T q2[2][Model::kNQMax];
+          Model::template site_chain_n<2>(p, tile, lane, site, s_theta + (size_t)ci * DS, WC * DS, q2);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            reduce_into<T, 0, Model::kNQMax>(q2[c], valid, lane, NQ, s_acc + ((size_t)ws * p.CB + ci + c * WC) * NQ);
+        }
+      }
+    }
+    for (; ci < ncb; ci += WC) {
+      T q[Model::kNQMax];
+      Model::site_chain(p, tile, lane, site, s_theta + (size_t)ci * DS, q);
+      reduce_into<T, 0, Model::kNQMax>(q, valid, lane, NQ, s_acc + ((size_t)ws * p.CB + ci) * NQ);
     }
     __syncthreads();  // every warp is done reading stage s
     if (tid == 0 && it + p.nstage < n_it) {
@@ -326,11 +355,22 @@ inline size_t eval_smem_bytes(const Layout& L, int elem, int WS, int nstage, int
 }
 
 inline Geometry plan_geometry(const Layout& L, int elem, int C, int D, int DS, int num_sms, int blocks_per_sm,
-                              size_t smem_limit) {
+                              size_t smem_limit, int wc_override = 0) {
   Geometry g{};
   g.n_chunks = (C + kMaxChainsPerBlock - 1) / kMaxChainsPerBlock;
   g.CB = (C + g.n_chunks - 1) / g.n_chunks;
-  g.WC = pow2_floor(g.CB < kWarpsPerBlock ? g.CB : kWarpsPerBlock);
+  // fewest chain-groups whose fp64 accumulators (WS x CB x NQ doubles) still fit beside the tile ring:
+  // WC = 1 keeps every warp busy for any CB (a warp walks all chains of the chunk on its own warp-tile)
+  // and stages 8 warp-tiles per TMA; larger chunks trade site-groups for accumulator space
+  const size_t acc_budget = smem_limit / blocks_per_sm / 3;
+  g.WC = 1;
+  while (g.WC < kWarpsPerBlock && (size_t)(kWarpsPerBlock / g.WC) * g.CB * (1 + D) * sizeof(double) > acc_budget)
+    g.WC *= 2;
+  // ... and wide units (many visits / fp64) trade them for a ring of at least two stages
+  while (g.WC < kWarpsPerBlock &&
+         eval_smem_bytes(L, elem, kWarpsPerBlock / g.WC, 2, g.CB, D, DS) > smem_limit / blocks_per_sm)
+    g.WC *= 2;
+  if (wc_override > 0) g.WC = wc_override;
   g.WS = kWarpsPerBlock / g.WC;
   g.n_block_tiles = (L.n_tiles + g.WS - 1) / g.WS;
   g.nstage = kMaxStages;

@@ -11,6 +11,7 @@ struct Plan {
   int occupancy;
   uint32_t rn_scratch_off;
   bool rn_global;  // occu_rn A_k scratch lives in global memory
+  int chain_bt;      // threads per block of the lane = chain variant (occu: 128 or 256)
   int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel; 2 / 3: occu_rn / occu_cop lane=chain kernels
 };
 }  // namespace bl

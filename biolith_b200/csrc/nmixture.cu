@@ -39,6 +39,7 @@ struct NmixModel {
   static constexpr int KOM = kGeneric ? kMaxCov : KO;
   static constexpr int kNQMax = 40;  // runtime NQ loop in the engine
   static constexpr int kDerived = 0;
+  static constexpr int kMultiChain = 1;  // chains per pass over a warp-tile (engine.cuh)
 
   struct Site {
     T x[KSM];

@@ -209,6 +209,113 @@ struct OccuModel {
       q[3 + ks + ko] = gx * d[6];
     }
   }
+
+  // NCH chains of the same warp-tile in one pass over the visits (no false-positive extras): the chains'
+  // dependent ex2 -> rcp -> lg2 sequences interleave (the engine is latency-bound at one chain per warp:
+  // 16 resident warps per SM), and every covariate is read from shared memory once for all of them.
+  // th0 + c * th_stride is the staged theta row of chain c; q[c] receives its NQ numbers.
+  static constexpr int kMultiChain = (FP || kGeneric) ? 1 : (sizeof(T) == 8 ? 2 : 4);  // register budget
+  template <int NCH>
+  static __device__ __forceinline__ void site_chain_n(const EvalParams& p, const T* __restrict__ tile, int lane,
+                                                      const Site& s, const T* __restrict__ th0, int th_stride,
+                                                      T (*__restrict__ q)[kNQMax]) {
+    static_assert(!FP, "multi-chain pass is for the plain model");
+    const int ks = kGeneric ? p.L.ks : KS;
+    const int ko = kGeneric ? p.L.ko : KO;
+    const int J = p.L.J;
+    T eta[NCH], a0[NCH], a[NCH][KOM], L1[NCH], ga0[NCH], ga[NCH][KOM];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const T* th = th0 + (size_t)c * th_stride;
+      eta[c] = th[0];
+#pragma unroll
+      for (int k = 0; k < KSM; ++k)
+        if (k < ks) eta[c] = N::fma_(s.x[k], th[1 + k], eta[c]);
+      a0[c] = th[ks + 1];
+#pragma unroll
+      for (int k = 0; k < KOM; ++k) {
+        a[c][k] = (k < ko) ? th[ks + 2 + k] : T(0);
+        ga[c][k] = T(0);
+      }
+      L1[c] = T(0);
+      ga0[c] = T(0);
+    }
+    uint32_t yw = 0, mw = 0;
+    const T* wrow = tile + p.L.off_w * kWarp + lane;
+#pragma unroll 2
+    for (int j = 0; j < J; ++j) {
+      if ((j & 31) == 0) {
+        yw = N::as_bits(tile[(p.L.off_y + (j >> 5)) * kWarp + lane]);
+        mw = N::as_bits(tile[(p.L.off_m + (j >> 5)) * kWarp + lane]);
+      }
+      const bool m = (mw >> (j & 31)) & 1u;
+      const bool y = (yw >> (j & 31)) & 1u;
+      T w[KOM];
+#pragma unroll
+      for (int k = 0; k < KOM; ++k) w[k] = (k < ko) ? wrow[(j * ko + k) * kWarp] : T(0);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        T nu = a0[c];
+#pragma unroll
+        for (int k = 0; k < KOM; ++k)
+          if (k < ko) nu = N::fma_(w[k], a[c][k], nu);
+        T term, g;
+        if constexpr (kSfu) {
+          const sfu::SoftSig ss = sfu::softsig<true>(nu);
+          const float yf = y ? 1.f : 0.f;
+          term = fmaf(yf, ss.xc, -ss.s);
+          g = ss.inr ? (yf - ss.p) : 0.f;
+        } else {
+          const LogSig<T> ls = log_sigmoid_pair<T>(nu);
+          term = y ? ls.lp : ls.l1mp;
+          g = ls.inr ? (y ? ls.q : -ls.p) : T(0);
+        }
+        term = m ? term : T(0);
+        g = m ? g : T(0);
+        L1[c] += term;
+        ga0[c] += g;
+#pragma unroll
+        for (int k = 0; k < KOM; ++k)
+          if (k < ko) ga[c][k] = N::fma_(g, w[k], ga[c][k]);
+      }
+    }
+    const T L0 = N::fma_(s.n1, N::log_tiny(), s.n0 * N::neg_tiny());
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      T ell, r, geta;
+      if constexpr (kSfu) {
+        const sfu::SoftSig se = sfu::softsig<true>(eta[c]);
+        const float av = (se.xc - se.s) + L1[c];
+        const float bv = L0 - se.s;
+        const float dd = av - bv;
+        const float td = sfu::ex2(-fabsf(dd) * sfu::kLog2e);
+        const float ud = 1.0f + td;
+        const float inv = sfu::rcp(ud);
+        r = (dd >= 0.f) ? inv : td * inv;
+        ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv));
+        geta = se.inr ? (r - se.p) : 0.f;
+      } else {
+        const LogSig<T> se = log_sigmoid_pair<T>(eta[c]);
+        const T av = se.lp + L1[c];
+        const T bv = se.l1mp + L0;
+        const T dd = av - bv;
+        const T td = N::exp_(-N::abs_(dd));
+        const T inv = N::rcp_(T(1) + td);
+        r = (dd >= T(0)) ? inv : td * inv;
+        ell = N::max_(av, bv) + N::log1p_(td);
+        geta = se.inr ? (r - se.p) : T(0);
+      }
+      q[c][0] = ell;
+      q[c][1] = geta;
+#pragma unroll
+      for (int k = 0; k < KSM; ++k)
+        if (k < ks) q[c][2 + k] = geta * s.x[k];
+      q[c][2 + ks] = r * ga0[c];
+#pragma unroll
+      for (int k = 0; k < KOM; ++k)
+        if (k < ko) q[c][3 + ks + k] = r * ga[c][k];
+    }
+  }
 };
 
 template <typename T, int KS, int KO, bool FP, bool STRICT, int MINB>
@@ -235,7 +342,7 @@ template <typename T, bool STRICT>
 static cudaError_t dispatch(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
   const int ks = p.L.ks, ko = p.L.ko;
   const bool fp = (p.flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) != 0;
-  constexpr int MB = sizeof(T) == 4 ? 3 : 2;
+  constexpr int MB = 2;  // 3 blocks/SM (<= 80 registers) spills 16 words and is no faster: the ring is sized for 2
   if (fp) return launch_one<T, -1, -1, true, true, 2>(p, grid, smem, st, occ);
   if (ks == 1 && ko == 1) return launch_one<T, 1, 1, false, STRICT, MB>(p, grid, smem, st, occ);
   if (ks == 2 && ko == 1) return launch_one<T, 2, 1, false, STRICT, MB>(p, grid, smem, st, occ);

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p
   const int c0 = blockIdx.y * p.CB;
   const int ncb = min(p.CB, p.C - c0);
   const bool chain_ok = tid < ncb;
+  const bool warp_on = (tid & ~31) < ncb;
   const int64_t nbt = p.n_block_tiles;
   const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
   const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
@@ -204,8 +205,10 @@ __global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p
     float acc[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
-    if (any_masked) chain_tile<KS, KO, NS, true, JT>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
-    else chain_tile<KS, KO, NS, false, JT>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
+    if (warp_on) {  // warps whose 32 lanes all lie past the end of the batch only help stage and expand
+      if (any_masked) chain_tile<KS, KO, NS, true, JT>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
+      else chain_tile<KS, KO, NS, false, JT>(tile, yfx, mfx, p.L, n_valid, b, a, acc, logp64);
+    }
 #pragma unroll
     for (int i = 1; i < NQ; ++i) g64[(size_t)i * BT] += (double)acc[i];
     __syncthreads();
@@ -252,12 +255,8 @@ bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
 
 // (NS, min blocks/SM) variants of the headline shape; BL_CHAIN_VARIANT picks one for tuning runs
 static int chain_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BL_CHAIN_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+  const char* e = getenv("BL_CHAIN_VARIANT");  // read per plan / launch: a tuning switch, not a hot path
+  return e ? atoi(e) : 0;
 }
 
 size_t occu_chain_smem(const Layout& L, int nstage, int block_threads) {
@@ -266,31 +265,41 @@ size_t occu_chain_smem(const Layout& L, int nstage, int block_threads) {
   return b + (size_t)(3 + kChainMaxKs + L.ko) * block_threads * sizeof(double);  // fp64 gradient columns
 }
 
-// threads per block (= chains per block) of the variant that launch_occu_chain will pick
-int occu_chain_block_threads(int ks, int ko) {
-  if (ks == 5 && ko == 3 && chain_variant() == 2) return 128;
-  return 256;
+// threads per block (= chains per block) for a batch of C chains.  A batch is cut into equal chunks of at
+// most one block and warps whose lanes all lie past the end of their chunk skip the arithmetic, so narrow
+// blocks waste fewer lanes on ragged batch sizes -- exactly the sizes the NUTS driver compacts to at the
+// tail of a run.  Measured on B200 (config 2, ms per evaluation, 128 / 256 threads): C=32 0.47 / 0.95,
+// 64 0.79 / 1.44, 128 1.42 / 1.49, 192 2.21 / 2.46, 384 3.67 / 5.24, 640 6.01 / 7.88; on whole multiples
+// of 256 the two agree within 1 % (1024: 9.16 for 256 threads with J compile-time) -> 256 only there.
+int occu_chain_block_threads(int ks, int ko, int C) {
+  (void)ks; (void)ko;
+  if (chain_variant() == 2) return 128;
+  if (chain_variant() == 3) return 256;
+  return (C > 0 && C % 256 == 0) ? 256 : 128;
+}
+
+template <int KS, int KO, int JT = 0>
+static cudaError_t launch_chain_bt(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  if (p.chain_bt == 128) return launch_chain_one<KS, KO, 4, 4, 128, JT>(p, grid, smem, st, occ);
+  return launch_chain_one<KS, KO, 4, 2, 256, JT>(p, grid, smem, st, occ);
 }
 
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
   const int ks = p.L.ks, ko = p.L.ko;
-  if (ks == 1 && ko == 1) return launch_chain_one<1, 1, 4, 2, 256>(p, grid, smem, st, occ);
-  if (ks == 2 && ko == 1) return launch_chain_one<2, 1, 4, 2, 256>(p, grid, smem, st, occ);
+  if (ks == 1 && ko == 1) return launch_chain_bt<1, 1>(p, grid, smem, st, occ);
+  if (ks == 2 && ko == 1) return launch_chain_bt<2, 1>(p, grid, smem, st, occ);
   if (ks == 5 && ko == 3) {
     // measured on B200 (config 2, ms per 1024-chain eval): J compile-time (8 visits fully unrolled) 9.16 |
     // runtime J unroll 2: 9.70, unroll 4: 10.35, unroll 1: 10.19 | 128 thr x 4 blocks: 9.79 |
     // 256 thr x 3 blocks (80 regs): 10.8 | 128 thr x 5 blocks (96 regs): 11.4 -> fewer, fatter warps win
-    const int v = chain_variant();
-    if (v == 2) return launch_chain_one<5, 3, 4, 4, 128>(p, grid, smem, st, occ);
-    if (v == 3) return launch_chain_one<5, 3, 4, 2, 256, 0>(p, grid, smem, st, occ);
-    if (p.L.J == 8) return launch_chain_one<5, 3, 4, 2, 256, 8>(p, grid, smem, st, occ);
-    return launch_chain_one<5, 3, 4, 2, 256>(p, grid, smem, st, occ);
+    if (p.L.J == 8 && chain_variant() != 3) return launch_chain_bt<5, 3, 8>(p, grid, smem, st, occ);
+    return launch_chain_bt<5, 3>(p, grid, smem, st, occ);
   }
   if (ks >= 0 && ks <= kChainMaxKs) {  // runtime Ks
-    if (ko == 1) return launch_chain_one<-1, 1, 4, 2, 256>(p, grid, smem, st, occ);
-    if (ko == 2) return launch_chain_one<-1, 2, 4, 2, 256>(p, grid, smem, st, occ);
-    if (ko == 3) return launch_chain_one<-1, 3, 4, 2, 256>(p, grid, smem, st, occ);
-    if (ko == 4) return launch_chain_one<-1, 4, 4, 2, 256>(p, grid, smem, st, occ);
+    if (ko == 1) return launch_chain_bt<-1, 1>(p, grid, smem, st, occ);
+    if (ko == 2) return launch_chain_bt<-1, 2>(p, grid, smem, st, occ);
+    if (ko == 3) return launch_chain_bt<-1, 3>(p, grid, smem, st, occ);
+    if (ko == 4) return launch_chain_bt<-1, 4>(p, grid, smem, st, occ);
   }
   return cudaErrorNotSupported;
 }

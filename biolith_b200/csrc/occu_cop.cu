@@ -9,6 +9,7 @@
 // are packed as (y, T) = (0, 0) and contribute exactly zero.  c = rate_fp_constant, u =
 // rate_fp_unoccupied enter through their logs (unconstrained ExpTransform space).
 // Closed form: oracle/occupancy.py:occu_cop_logp_grad.
+#include <cstdlib>
 #include <type_traits>
 
 #include "engine.cuh"
@@ -25,6 +26,7 @@ struct OccuCopModel {
   static constexpr int KOM = kGeneric ? kMaxCov : KO;
   static constexpr int kNQMax = 40;   // runtime NQ loop in the engine
   static constexpr int kDerived = 6;  // c, u, rho0, log rho0, 1/rho0, -
+  static constexpr int kMultiChain = 1;  // chains per pass over a warp-tile (engine.cuh)
 
   struct Site {
     T x[KSM];
@@ -155,7 +157,7 @@ struct OccuCopModel {
 // rate -> 3 MUFU like the Bernoulli kernel.
 // ------------------------------------------------------------------------------------------------
 template <int KS, int KO, int BT, int JT>
-__global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_cop_chain_kernel(const EvalParams p) {
   // KS < 0: runtime number of site covariates (<= 8); accumulator slots are laid out for the capacity
   constexpr int KSM = KS < 0 ? 8 : KS;
   constexpr int KB = KSM + 1, KA = KO + 1, NS = 4, NQM = 1 + KB + KA + 2;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
   const int c0 = blockIdx.y * p.CB;
   const int ncb = min(p.CB, p.C - c0);
   const bool chain_ok = tid < ncb;
+  const bool warp_on = (tid & ~31) < ncb;  // warps past the end of the batch only help stage the tiles
   const int64_t nbt = p.n_block_tiles;
   const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
   const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
     float acc[NQM];
 #pragma unroll
     for (int i = 0; i < NQM; ++i) acc[i] = 0.f;
-    for (int g0 = 0; g0 < n_valid; g0 += NS) {
+    const int n_mine = warp_on ? n_valid : 0;
+    for (int g0 = 0; g0 < n_mine; g0 += NS) {
       float eta[NS], geta[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) eta[i] = b[0];
@@ -340,33 +344,51 @@ __global__ void __launch_bounds__(BT, 2) occu_cop_chain_kernel(const EvalParams 
   finish_block<float>(p, c0, ncb, &s_is_last);
 }
 
-constexpr int kCopChainThreads = 256;
+static int cop_chain_variant() {
+  const char* e = getenv("BL_CHAIN_VARIANT");  // tuning switch: 2 = 128-thread blocks, 3 = 256-thread blocks
+  return e ? atoi(e) : 0;
+}
 
 bool occu_cop_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
   return (ks == 5 && ko == 3) || (ks >= 0 && ks <= 8 && ko >= 1 && ko <= 4);
 }
 
-int occu_cop_chain_block_threads() { return kCopChainThreads; }
-
-size_t occu_cop_chain_smem(const Layout& L, int nstage) {
-  size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float);
-  bts = (bts + 15) & ~size_t(15);
-  return bts + (size_t)(5 + 8 + L.ko) * kCopChainThreads * sizeof(double);
+// threads (= chains) per block for a batch of C chains; see occu_chain.cu:occu_chain_block_threads.
+// Measured on B200 (config 4, ms per evaluation, 128 / 256 threads): C=32 0.36 / 0.59, 64 0.58 / 0.91,
+// 96 0.94 / 0.94, 128 1.11 / 0.96, 192 1.59 / 1.77, 256 1.84 / 1.82, 384 2.64 / 3.38, 512 3.46 / 3.41,
+// 1024 6.77 / 6.70 (site-parallel engine: 32 0.45, 64 0.87, 128 1.70).
+int occu_cop_chain_block_threads(int C) {
+  if (cop_chain_variant() == 2) return 128;
+  if (cop_chain_variant() == 3) return 256;
+  if (C > 64 && C <= 128) return 256;
+  return (C > 0 && C % 256 == 0) ? 256 : 128;
 }
 
-template <int KS, int KO, int JT>
-static cudaError_t launch_cop_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = occu_cop_chain_kernel<KS, KO, kCopChainThreads, JT>;
+size_t occu_cop_chain_smem(const Layout& L, int nstage, int bt) {
+  size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float);
+  bts = (bts + 15) & ~size_t(15);
+  return bts + (size_t)(5 + 8 + L.ko) * bt * sizeof(double);
+}
+
+template <int KS, int KO, int JT, int BT>
+static cudaError_t launch_cop_chain_bt(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  auto kern = occu_cop_chain_kernel<KS, KO, BT, JT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kCopChainThreads, smem);
-  kern<<<grid, kCopChainThreads, smem, st>>>(p);
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, BT, smem);
+  kern<<<grid, BT, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int KS, int KO, int JT>
+static cudaError_t launch_cop_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  if (p.chain_bt == 128) return launch_cop_chain_bt<KS, KO, JT, 128>(p, grid, smem, st, occ);
+  return launch_cop_chain_bt<KS, KO, JT, 256>(p, grid, smem, st, occ);
 }
 
 cudaError_t launch_occu_cop_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {

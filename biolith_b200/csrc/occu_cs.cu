@@ -34,6 +34,7 @@ struct OccuCsModel {
   static constexpr int kNQMax = kGeneric ? 40 : (1 + KS + 1 + KO + 1 + 4);
   // derived per-chain slots after the D raw parameters: mu1, 1/sigma0, 1/sigma1, exp(x1)
   static constexpr int kDerived = 4;
+  static constexpr int kMultiChain = 1;  // chains per pass over a warp-tile (engine.cuh)
 
   struct Site {
     T x[KSM];

@@ -12,6 +12,7 @@
 // 1-(1-r)**N cancellation of the reference formulation (oracle/occupancy.py:occu_rn_logp_grad).
 // Per-thread state A_k lives in shared memory ([K+1][256], conflict-free), visits outer / k inner.
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -33,6 +34,7 @@ struct OccuRnModel {
   static constexpr int KOM = kGeneric ? kMaxCov : KO;
   static constexpr int kNQMax = kGeneric ? (1 + 2 * (kMaxCov + 1) + 1) : 33;  // runtime NQ loop either way
   static constexpr int kDerived = 4;  // l1mc = log(1-c), c, 1-c, dc/dx = c(1-c)
+  static constexpr int kMultiChain = 1;  // chains per pass over a warp-tile (engine.cuh)
 
   struct Site {
     T x[KSM];
@@ -242,7 +244,7 @@ struct OccuRnModel {
 // RT = true: KS / KO are capacities and the actual covariate counts come from the layout (the k-loops
 // dominate, so the predicated site-level loops cost nothing measurable)
 template <int KS, int KO, int BT, bool RT>
-__global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_rn_chain_kernel(const EvalParams p) {
   using N = Num<float>;
   using M = Mth<float, true>;
   constexpr int KB = KS + 1, KA = KO + 1;
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
   const int c0 = blockIdx.y * p.CB;
   const int ncb = min(p.CB, p.C - c0);
   const bool chain_ok = tid < ncb;
+  const bool warp_on = (tid & ~31) < ncb;  // warps past the end of the batch only help stage and expand
   const int64_t nbt = p.n_block_tiles;
   const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
   const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
@@ -323,7 +326,8 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
 #pragma unroll
     for (int k = 0; k < KA; ++k) acc_ga[k] = 0.f;
 
-    for (int si = 0; si < n_valid; ++si) {
+    const int n_mine = warp_on ? n_valid : 0;
+    for (int si = 0; si < n_mine; ++si) {
       float x[KS > 0 ? KS : 1];
       float eta = b[0];
 #pragma unroll
@@ -548,34 +552,52 @@ __global__ void __launch_bounds__(BT, 2) occu_rn_chain_kernel(const EvalParams p
   finish_block<float>(p, c0, ncb, &s_is_last);
 }
 
-constexpr int kRnChainThreads = 256;
+static int rn_chain_variant() {
+  const char* e = getenv("BL_CHAIN_VARIANT");  // tuning switch: 2 = 128-thread blocks, 3 = 256-thread blocks
+  return e ? atoi(e) : 0;
+}
 
 bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
   return ks >= 0 && ks <= 8 && ko >= 0 && ko <= 4;  // (5,3) specialised, the rest through the capacity variant
 }
 
-int occu_rn_chain_block_threads() { return kRnChainThreads; }
-
-size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D) {
-  size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
-  bts = (bts + 15) & ~size_t(15);
-  bts += (size_t)(1 + D) * kRnChainThreads * sizeof(double);
-  return bts + (size_t)(K + 1 + L.J) * kRnChainThreads * sizeof(float);
+// threads (= chains) per block for a batch of C chains; see occu_chain.cu:occu_chain_block_threads.  The
+// per-thread A_k / U0 columns make 128-thread blocks 10 % slower on full batches, so they are used only
+// where they pad the batch less.  Measured on B200 (config 3, K = 50, ms per evaluation, 128 / 256 threads):
+// C=32 9.1 / 13.3, 64 10.8 / 15.9, 128 13.1 / 15.9, 192 25.2 / 23.3, 256 25.2 / 23.4, 384 37.9 / 45.0,
+// 512 49.7 / 45.1, 1024 99.5 / 89.1 (site-parallel engine: 32 14.7, 64 29.5, 128 53.8).
+int occu_rn_chain_block_threads(int C) {
+  if (rn_chain_variant() == 2) return 128;
+  if (rn_chain_variant() == 3) return 256;
+  return (C > 128 && (C + 127) / 128 % 2 == 0) ? 256 : 128;
 }
 
-template <int KS, int KO, bool RT>
+size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D, int bt) {
+  size_t bts = 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
+  bts = (bts + 15) & ~size_t(15);
+  bts += (size_t)(1 + D) * bt * sizeof(double);
+  return bts + (size_t)(K + 1 + L.J) * bt * sizeof(float);
+}
+
+template <int KS, int KO, int BT, bool RT>
 static cudaError_t launch_rn_chain_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = occu_rn_chain_kernel<KS, KO, kRnChainThreads, RT>;
+  auto kern = occu_rn_chain_kernel<KS, KO, BT, RT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kRnChainThreads, smem);
-  kern<<<grid, kRnChainThreads, smem, st>>>(p);
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, BT, smem);
+  kern<<<grid, BT, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int KS, int KO, bool RT>
+static cudaError_t launch_rn_chain_bt(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  if (p.chain_bt == 128) return launch_rn_chain_one<KS, KO, 128, RT>(p, grid, smem, st, occ);
+  return launch_rn_chain_one<KS, KO, 256, RT>(p, grid, smem, st, occ);
 }
 
 static cudaError_t ensure_lgamma_table();
@@ -585,8 +607,8 @@ cudaError_t launch_occu_rn_chain(const EvalParams& p, dim3 grid, size_t smem, cu
     cudaError_t e = ensure_lgamma_table();
     if (e != cudaSuccess) return e;
   }
-  if (p.L.ks == 5 && p.L.ko == 3) return launch_rn_chain_one<5, 3, false>(p, grid, smem, st, occ);
-  if (p.L.ks <= 8 && p.L.ko <= 4) return launch_rn_chain_one<8, 4, true>(p, grid, smem, st, occ);
+  if (p.L.ks == 5 && p.L.ko == 3) return launch_rn_chain_bt<5, 3, false>(p, grid, smem, st, occ);
+  if (p.L.ks <= 8 && p.L.ko <= 4) return launch_rn_chain_bt<8, 4, true>(p, grid, smem, st, occ);
   return cudaErrorNotSupported;
 }
 

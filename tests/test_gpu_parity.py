@@ -54,7 +54,7 @@ def test_golden_parity(name, dtype):
         assert_close(lp, gr, g[f"loglik_{mode}"], g[f"gradlik_{mode}"], RTOL[dtype], f"{name}/{dtype}/lik")
 
 
-@pytest.mark.parametrize("n_chains", [1, 2, 3, 5, 8, 31, 64, 127, 128, 257, 700])
+@pytest.mark.parametrize("n_chains", [1, 2, 3, 5, 8, 16, 31, 32, 33, 64, 96, 127, 128, 129, 192, 256, 257, 384, 700])
 def test_chain_batching_is_consistent(n_chains):
     """Every (C -> WS x WC arrangement, chunking) must give the same per-chain numbers."""
     from oracle import occupancy as orc
@@ -230,7 +230,7 @@ def test_strict_math_flag(name):
 @pytest.mark.parametrize("ks,ko,K,fpc", [(1, 1, 100, False), (5, 3, 50, False), (5, 3, 30, True), (1, 1, 12, True),
                                           (0, 0, 20, False), (8, 4, 25, True), (3, 2, 40, False)])
 def test_rn_chain_kernel_against_oracle(ks, ko, K, fpc):
-    """The lane=chain Royle-Nichols kernel (C >= 64): ragged visits, NaN covariates, clamp-active
+    """The lane=chain Royle-Nichols kernel (C >= 32): ragged visits, NaN covariates, clamp-active
     states (r close to 1 makes k*log(1-r) cross log eps), optional false-positive constant."""
     import biolith_b200 as bb
     from oracle import occupancy as orc
@@ -251,14 +251,18 @@ def test_rn_chain_kernel_against_oracle(ks, ko, K, fpc):
     with bb.OccupancyLikelihood("occu_rn", X, W, y, max_abundance=K, false_positives_constant=fpc) as lk:
         lp, gr = lk.logp_and_grad(th)
         assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"rn chain ks={ks} K={K} fpc={fpc}")
-        lp_e, gr_e = lk.logp_and_grad(th[:8])  # same handle, site-parallel engine (C < 64)
+        lp_e, gr_e = lk.logp_and_grad(th[:8])  # same handle, site-parallel engine (C < 32)
         np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
+        for n in (40, 128, 150):  # 128- and 256-thread chain blocks, partly idle warps
+            lp_s, gr_s = lk.logp_and_grad(th[:n])
+            np.testing.assert_allclose(lp_s, lp[:n], rtol=5e-6)
+            np.testing.assert_allclose(gr_s, gr[:n], rtol=1e-4, atol=1e-5 * np.abs(gr).max())
 
 
 @pytest.mark.parametrize("ks,ko,fpc,fpu", [(1, 1, True, False), (5, 3, True, True), (5, 3, False, False), (1, 1, False, True),
                                            (0, 2, True, False), (8, 4, True, True), (3, 1, False, False)])
 def test_cop_chain_kernel_against_oracle(ks, ko, fpc, fpu):
-    """The lane=chain count-detection kernel (C >= 64): ragged / missing visits, varying exposure, every
+    """The lane=chain count-detection kernel (C >= 32): ragged / missing visits, varying exposure, every
     false-positive configuration (without any, a unit that saw a count is occupied with certainty)."""
     import biolith_b200 as bb
     from oracle import occupancy as orc
@@ -284,6 +288,10 @@ def test_cop_chain_kernel_against_oracle(ks, ko, fpc, fpu):
         assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"cop chain ks={ks} fpc={fpc} fpu={fpu}")
         lp_e, gr_e = lk.logp_and_grad(th[:8])  # site-parallel engine on the same handle
         np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
+        for n in (40, 100, 128):  # 128- and 256-thread chain blocks, partly idle warps
+            lp_s, gr_s = lk.logp_and_grad(th[:n])
+            np.testing.assert_allclose(lp_s, lp[:n], rtol=5e-6)
+            np.testing.assert_allclose(gr_s, gr[:n], rtol=1e-4, atol=1e-5 * np.abs(gr).max())
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
