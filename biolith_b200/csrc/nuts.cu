@@ -732,10 +732,11 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
     CU_TRY(cudaMemcpyAsync(&done, p.n_done, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
     if (done >= p.C) break;
-    // compaction: evaluate only the chains that are still running (whole 128-chain steps)
+    // compaction: evaluate only the chains that are still running, in whole warps (the lane = chain kernels
+    // skip warps past the end of the batch, so a 32-chain granularity is what the tail of a run pays for)
     if (s->compaction) {
       const int active = p.C - done;
-      const int rows = std::min(p.C, (active + 127) / 128 * 128);
+      const int rows = std::min(p.C, (active + 31) / 32 * 32);
       if (rows < s->n_rows) {
         if (f32) nuts_compact_kernel<float><<<1, 1024, 0, s->stream>>>(p);
         else nuts_compact_kernel<double><<<1, 1024, 0, s->stream>>>(p);
