@@ -1,5 +1,5 @@
 """Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck).
-usage: sanitize.py [model ...]   (default: all four)"""
+usage: sanitize.py [model ...]   (default: all five)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,7 +7,7 @@ import biolith_b200 as bb
 
 rng = np.random.default_rng(0)
 ALL = {"occu": {}, "occu_rn": dict(max_abundance=12), "occu_cop": dict(false_positives_constant=True),
-       "nmixture": dict(max_abundance=80)}
+       "nmixture": dict(max_abundance=80), "occu_cs": {}}
 todo = sys.argv[1:] or list(ALL)
 S = int(os.environ.get("SANITIZE_SITES", "333"))
 for model in todo:
@@ -16,7 +16,8 @@ for model in todo:
                                     simulate_missing=True, random_seed=1)
     T = data.get("session_duration")
     with bb.OccupancyLikelihood(model, data["site_covs"], data["obs_covs"], data["obs"], T, **kw) as lk:
-        for C in (3, 130):  # site-parallel engine, chain-parallel kernels
+        # site-parallel engine (1, 2 and 4 chains per pass), chain kernels with 128- and 256-thread blocks
+        for C in (3, 7, 40, 130, 256):
             lp, gr = lk.logp_and_grad(rng.uniform(-1, 1, size=(C, lk.theta_dim)))
             assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr))
         lk.site_summary(rng.uniform(-1, 1, size=(5, lk.theta_dim)))
