@@ -45,6 +45,11 @@ WORKLOADS = {
                                              deployment_days_per_site=70), 256, "chains"),
     "occu_cop_500k_x12": ("occu_cop", dict(n_site_covs=5, n_obs_covs=3, n_sites=500_000,
                                            deployment_days_per_site=84, simulate_missing=True), 1024, "chains"),
+    # SURVEY 8 row f4 siblings (site-parallel engine only), timed for DESIGN.md
+    "nmixture_200k_x10": ("nmixture", dict(n_site_covs=5, n_obs_covs=3, n_sites=200_000,
+                                           deployment_days_per_site=70), 256, "chains"),
+    "occu_cs_500k_x10": ("occu_cs", dict(n_site_covs=5, n_obs_covs=3, n_sites=500_000,
+                                         deployment_days_per_site=70), 256, "chains"),
 }
 MODEL_KW = {"occu_rn": dict(max_abundance=50), "occu_cop": dict(false_positives_constant=True)}
 METRIC = "logp+grad evals/sec (occu, 1M sites x 8 visits, chain-batched)"
@@ -206,6 +211,8 @@ def main():
     model, X, W, y, chains, shard = make_data(args.workload, 0 if shard_is_chains(args.workload) else rank)
     if args.chains:
         chains = args.chains
+    if model == "nmixture":  # truncation point: comfortably above the largest count (nmixture.py:24)
+        MODEL_KW["nmixture"] = dict(max_abundance=int(np.nanmax(y)) + 10)
     comm = None
     lk = bb.OccupancyLikelihood(model, X, W, y, make_data.session_duration, dtype=args.dtype, device=local_rank,
                                 max_chains=chains, strict_math=args.strict_math, **MODEL_KW.get(model, {}))

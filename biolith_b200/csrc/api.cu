@@ -50,6 +50,7 @@ bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 size_t occu_chain_smem(const Layout& L, int nstage, int block_threads);
 int occu_chain_block_threads(int ks, int ko, int C);
+int occu_chain_variant();
 bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 int occu_rn_chain_block_threads(int C);
 size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D, int bt);
@@ -58,6 +59,11 @@ bool occu_cop_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 int occu_cop_chain_block_threads(int C);
 size_t occu_cop_chain_smem(const Layout& L, int nstage, int bt);
 cudaError_t launch_occu_cop_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
+
+bool occu_cs_chain_supported(int dtype, int ks, int ko, uint32_t flags);
+int occu_cs_chain_block_threads(int C);
+size_t occu_cs_chain_smem(const Layout& L, int nstage, int bt);
+cudaError_t launch_occu_cs_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
@@ -99,7 +105,6 @@ static void fill_params(const bl_dataset* ds, EvalParams& p) {
   p.prior_fp_b = ds->desc.prior_fp_b;
   p.prior_fp_rate = ds->desc.prior_fp_rate;
   p.nch = 4;
-  if (const char* ev = getenv("BL_ENGINE_NCH")) p.nch = atoi(ev);
 }
 
 // geometry for C chains (cached); grows the fp64 partial workspace when needed
@@ -130,6 +135,8 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
         wc = !strcmp(ev, "old") ? pow2_floor(C < kWarpsPerBlock ? (C < 1 ? 1 : C) : kWarpsPerBlock) : atoi(ev);
       pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, bps, ds->smem_limit, wc);
     }
+    pl.nch = 4;  // chains a warp interleaves per pass (models that implement site_chain_n)
+    if (const char* ev = getenv("BL_ENGINE_NCH")) pl.nch = atoi(ev) > 0 ? atoi(ev) : pl.nch;
     pl.rn_scratch_off = (uint32_t)((pl.g.smem_bytes + 127) & ~size_t(127));
     pl.g.smem_bytes = pl.rn_scratch_off + extra;
     int chain_min = kChainKernelMinChains;
@@ -146,11 +153,17 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     if (want_chain && ds->desc.model == BL_MODEL_OCCU_COP &&
         occu_cop_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
       pl.chain_kernel = 3;
+    // occu_cs: the engine wins below 64 chains (B200, 500k x 10: 32 chains 0.71 vs 1.04 ms, 64: 1.41 vs 1.43)
+    if (want_chain && C >= 64 && ds->desc.model == BL_MODEL_OCCU_CS &&
+        occu_cs_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
+      pl.chain_kernel = 4;
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
       const int bt = pl.chain_kernel == 1   ? occu_chain_block_threads(ds->L.ks, ds->L.ko, C)
                      : pl.chain_kernel == 2 ? occu_rn_chain_block_threads(C)
-                                            : occu_cop_chain_block_threads(C);  // chains per block
+                     : pl.chain_kernel == 3 ? occu_cop_chain_block_threads(C)
+                                            : occu_cs_chain_block_threads(C);  // chains per block
       pl.chain_bt = bt;
+      pl.chain_variant = occu_chain_variant();
       pl.g.n_chunks = (C + bt - 1) / bt;
       pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
       pl.g.WS = 1; pl.g.WC = kWarpsPerBlock;
@@ -160,6 +173,8 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
         pl.g.smem_bytes = occu_chain_smem(ds->L, pl.g.nstage, bt);
       } else if (pl.chain_kernel == 3) {
         pl.g.smem_bytes = occu_cop_chain_smem(ds->L, pl.g.nstage, bt);
+      } else if (pl.chain_kernel == 4) {
+        pl.g.smem_bytes = occu_cs_chain_smem(ds->L, pl.g.nstage, bt);
       } else {
         while (pl.g.nstage > 2 &&
                occu_rn_chain_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, ds->D, bt) > ds->smem_limit)
@@ -174,10 +189,13 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     EvalParams p;
     fill_params(ds, p);
     p.chain_bt = pl.chain_bt;
+    p.chain_variant = pl.chain_variant;
+    p.nch = pl.nch;
     int occ = 0;
     cudaError_t e = pl.chain_kernel == 1   ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 2 ? launch_occu_rn_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 3 ? launch_occu_cop_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                    : pl.chain_kernel == 4 ? launch_occu_cs_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                                            : launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
     if (e != cudaSuccess) return fail(BL_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (occ < 1) return fail(BL_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", pl.g.smem_bytes);
@@ -247,6 +265,8 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.WS = pl->g.WS;
   p.nstage = pl->g.nstage;
   p.chain_bt = pl->chain_bt;
+  p.chain_variant = pl->chain_variant;
+  p.nch = pl->nch;
   p.nsplit = pl->g.nsplit;
   p.n_block_tiles = pl->g.n_block_tiles;
   p.rn_scratch_off = pl->rn_scratch_off;
@@ -255,6 +275,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   cudaError_t e = pl->chain_kernel == 1   ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 2 ? launch_occu_rn_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 3 ? launch_occu_cop_chain(p, grid, pl->g.smem_bytes, st, nullptr)
+                  : pl->chain_kernel == 4 ? launch_occu_cs_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                                           : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
   if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);

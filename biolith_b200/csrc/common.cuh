@@ -330,6 +330,7 @@ struct EvalParams {
   double cop_const;  // occu_cop: sum_s sum_j m (y log T - lgamma(y+1)), data-only
   double prior_beta_loc, prior_beta_scale, prior_alpha_loc, prior_alpha_scale;
   double prior_fp_a, prior_fp_b, prior_fp_rate;
+  int chain_variant;  // BL_CHAIN_VARIANT tuning switch as read at plan time (3 = runtime-J kernel)
   int chain_bt;   // lane = chain kernels: threads (= chains) per block of the selected variant
   int nch;        // engine: chains a warp interleaves per pass over a warp-tile (1, 2 or 4)
   int allreduce;  // 0 none; 1 = leave raw sums in `sums` for a collective, finalize separately

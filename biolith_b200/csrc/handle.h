@@ -11,8 +11,10 @@ struct Plan {
   int occupancy;
   uint32_t rn_scratch_off;
   bool rn_global;  // occu_rn A_k scratch lives in global memory
+  int nch;           // site-parallel engine: chains interleaved per pass over a warp-tile
+  int chain_variant; // BL_CHAIN_VARIANT as read when the plan was made
   int chain_bt;      // threads per block of the lane = chain variant (occu: 128 or 256)
-  int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel; 2 / 3: occu_rn / occu_cop lane=chain kernels
+  int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel; 2 / 3 / 4: occu_rn / occu_cop / occu_cs lane=chain kernels
 };
 }  // namespace bl
 

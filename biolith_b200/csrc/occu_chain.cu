@@ -255,9 +255,11 @@ bool occu_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
 
 // (NS, min blocks/SM) variants of the headline shape; BL_CHAIN_VARIANT picks one for tuning runs
 static int chain_variant() {
-  const char* e = getenv("BL_CHAIN_VARIANT");  // read per plan / launch: a tuning switch, not a hot path
+  const char* e = getenv("BL_CHAIN_VARIANT");  // tuning switch, read when a plan is made (never per launch)
   return e ? atoi(e) : 0;
 }
+
+int occu_chain_variant() { return chain_variant(); }
 
 size_t occu_chain_smem(const Layout& L, int nstage, int block_threads) {
   size_t b = 128 + (size_t)nstage * L.F * kWarp * sizeof(float) + 2 * (size_t)L.J * kWarp * sizeof(float);
@@ -292,7 +294,7 @@ cudaError_t launch_occu_chain(const EvalParams& p, dim3 grid, size_t smem, cudaS
     // measured on B200 (config 2, ms per 1024-chain eval): J compile-time (8 visits fully unrolled) 9.16 |
     // runtime J unroll 2: 9.70, unroll 4: 10.35, unroll 1: 10.19 | 128 thr x 4 blocks: 9.79 |
     // 256 thr x 3 blocks (80 regs): 10.8 | 128 thr x 5 blocks (96 regs): 11.4 -> fewer, fatter warps win
-    if (p.L.J == 8 && chain_variant() != 3) return launch_chain_bt<5, 3, 8>(p, grid, smem, st, occ);
+    if (p.L.J == 8 && p.chain_variant != 3) return launch_chain_bt<5, 3, 8>(p, grid, smem, st, occ);
     return launch_chain_bt<5, 3>(p, grid, smem, st, occ);
   }
   if (ks >= 0 && ks <= kChainMaxKs) {  // runtime Ks

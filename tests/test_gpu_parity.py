@@ -346,3 +346,37 @@ def test_chain_kernel_runtime_ks_variants(ks, ko):
     with bb.OccupancyLikelihood("occu", X, W, y) as lk:
         lp, gr = lk.logp_and_grad(th)
         assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"runtime-Ks chain ks={ks} ko={ko}")
+
+
+@pytest.mark.parametrize("ks,ko", [(1, 1), (5, 3), (0, 2), (8, 4), (3, 1), (2, 3)])
+def test_cs_chain_kernel_against_oracle(ks, ko):
+    """The lane=chain continuous-score kernel (C >= 32): ragged / missing visits, NaN covariates, score
+    parameters from far off (sigma = e^-1.5: |n1 - n0| in the thousands) to the generating values."""
+    import biolith_b200 as bb
+    from oracle import occupancy as orc
+
+    rng = np.random.default_rng(ks * 7 + ko)
+    S, J = 171, 9
+    X = rng.normal(size=(S, ks))
+    W = rng.normal(size=(S, 1, J, ko))
+    occ = rng.uniform(size=(1, S, 1, 1)) < 0.5
+    f = (rng.uniform(size=(1, S, 1, J)) < 0.4) & occ
+    y = np.where(f, rng.normal(10, 5, size=f.shape), rng.normal(0, 10, size=f.shape))
+    lens = rng.integers(0, J + 1, size=S)
+    y[0, :, 0][np.arange(J)[None, :] >= lens[:, None]] = np.nan
+    W[rng.uniform(size=W.shape) < 0.03] = np.nan
+    D = ks + ko + 6
+    th = rng.uniform(-1.5, 1.5, size=(300, D))
+    th[::3, -4:] = np.array([0.0, np.log(10.0), np.log(10.0), np.log(5.0)]) + 0.1 * rng.standard_normal((100, 4))
+    pr = orc.prepare(X, W, y)
+    idx = [0, 1, 2, 50, 131, 299]
+    ref_lp, ref_gr = orc.logp_grad("occu_cs", th[idx], pr)
+    with bb.OccupancyLikelihood("occu_cs", X, W, y) as lk:
+        lp, gr = lk.logp_and_grad(th)  # 300 chains: three 128-thread chunks of 100
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"cs chain ks={ks} ko={ko}")
+        lp_e, gr_e = lk.logp_and_grad(th[:8])  # site-parallel engine on the same handle
+        np.testing.assert_allclose(lp_e, lp[:8], rtol=5e-6)
+        for n in (40, 128, 256):  # 128- and 256-thread chain blocks, partly idle warps
+            lp_s, gr_s = lk.logp_and_grad(th[:n])
+            np.testing.assert_allclose(lp_s, lp[:n], rtol=5e-6)
+            np.testing.assert_allclose(gr_s, gr[:n], rtol=1e-4, atol=1e-5 * np.abs(gr).max())
