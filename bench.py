@@ -425,9 +425,9 @@ def shard_is_chains(workload):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the eval kernel (ncu --set full), by workload
 PROFILED_TRAFFIC = {
-    # profiles/r01_occu_chain_v5.txt: 230.99 MB read + 10.07 MB written per launch (packed dataset: 128 MB;
-    # the 4 chain chunks re-read tiles mostly from L2)
-    "occu_1m_x8_c1024": 241_061_376,
+    # profiles/r01_occu_chain_v6.txt (final round-1 binary): 227.34 MB read + 9.17 MB written per launch
+    # (packed dataset: 128 MB; the 4 chain chunks re-read tiles mostly from L2)
+    "occu_1m_x8_c1024": 236_505_600,
 }
 
 
