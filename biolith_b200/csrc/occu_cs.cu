@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_cs_chain_kernel(co
 
 bool occu_cs_chain_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32 || (flags & BL_FLAG_STRICT_MATH)) return false;
-  if (const char* e = getenv("BL_CS_CHAIN")) return atoi(e) != 0;  // tuning switch: 0 forces the engine
+  if (const char* e = getenv("BL_CS_CHAIN"))
+    if (atoi(e) == 0) return false;  // tuning switch: 0 forces the site-parallel engine
   return ks >= 0 && ks <= 8 && ko >= 1 && ko <= 4;
 }
 
