@@ -380,3 +380,46 @@ def test_cs_chain_kernel_against_oracle(ks, ko):
             lp_s, gr_s = lk.logp_and_grad(th[:n])
             np.testing.assert_allclose(lp_s, lp[:n], rtol=5e-6)
             np.testing.assert_allclose(gr_s, gr[:n], rtol=1e-4, atol=1e-5 * np.abs(gr).max())
+
+
+@pytest.mark.parametrize("model,sim_kw,model_kw", [
+    ("occu_rn", dict(n_sites=200_000, deployment_days_per_site=70), dict(max_abundance=50)),
+    ("occu_cop", dict(n_sites=500_000, deployment_days_per_site=84, simulate_missing=True),
+     dict(false_positives_constant=True)),
+    ("occu_cs", dict(n_sites=500_000, deployment_days_per_site=70), {}),
+    ("nmixture", dict(n_sites=200_000, deployment_days_per_site=70), dict(max_abundance=80)),
+])
+def test_full_size_site_split_additivity(model, sim_kw, model_kw):
+    """BASELINE configs 3 / 4 (and the two siblings at the same scale) at FULL size, through a
+    size-independent property: the log-likelihood and its gradient are sums over sites, so evaluating two
+    site blocks on their own handles and adding must reproduce the whole (40 chains: the lane=chain kernels
+    for occu_rn / occu_cop, the site-parallel engine for the siblings)."""
+    import biolith_b200 as bb
+    from biolith_b200.simulate import simulate_occupancy
+
+    data, _ = simulate_occupancy(model, n_site_covs=5, n_obs_covs=3, random_seed=0, **sim_kw)
+    X = data["site_covs"].astype(np.float32)
+    W = data["obs_covs"].astype(np.float32)
+    y = data["obs"].astype(np.float32)
+    T = data.get("session_duration")
+    T = None if T is None else T.astype(np.float32)
+    S = X.shape[0]
+    rng = np.random.default_rng(3)
+
+    def make(sl):
+        return bb.OccupancyLikelihood(model, X[sl], W[sl], y[:, sl], None if T is None else T[sl], prior=False,
+                                      **model_kw)
+
+    with make(slice(None)) as full:
+        D = full.theta_dim
+        th = rng.uniform(-1, 1, size=(40, D))
+        if model == "occu_cs":
+            th[:, -4:] = np.array([0.0, np.log(10.0), np.log(10.0), np.log(5.0)]) + 0.1 * rng.standard_normal((40, 4))
+        lp, gr = full.logp_and_grad(th)
+    h = S // 3
+    with make(slice(0, h)) as a, make(slice(h, S)) as b:
+        la, ga = a.logp_and_grad(th)
+        lb, gb = b.logp_and_grad(th)
+    assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr))
+    np.testing.assert_allclose(la.astype(np.float64) + lb, lp, rtol=5e-6)
+    np.testing.assert_allclose(ga.astype(np.float64) + gb, gr, rtol=1e-4, atol=2e-5 * np.abs(gr).max())
