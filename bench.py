@@ -364,8 +364,8 @@ def main():
             line["exchange_check"] = exchange_check
         if nuts is not None:
             line["nuts"] = nuts
-        if not args.no_cpu_baseline and world == 1 and model == "occu":
-            line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains)
+        if not args.no_cpu_baseline and world == 1 and model in ("occu", "occu_cop"):
+            line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains, model, make_data.session_duration)
         print(json.dumps(_finite(line)), flush=True)
     lk.close()
     if dist is not None:
@@ -444,20 +444,28 @@ PROFILED_TRAFFIC = {
 }
 
 
-def cpu_baseline(X, W, y, D, sample):
+def cpu_baseline(X, W, y, D, sample, model="occu", T=None):
     from oracle import c_oracle
 
     threads = c_oracle.max_threads()
     th = np.random.default_rng(1).uniform(-2, 2, size=(sample, D))
-    c_oracle.occu_logp_grad(th[:1], X, W, y)
+    if model == "occu_cop":  # config 4: the C restatement computes in double (clamp constants of fp32)
+        def run(t):
+            return c_oracle.occu_cop_logp_grad(t, X, W, y, T, fp_constant=True)
+        arith = "fp64-arithmetic"
+    else:
+        def run(t):
+            return c_oracle.occu_logp_grad(t, X, W, y)
+        arith = "fp32"
+    run(th[:1])
     t0 = time.perf_counter()
     reps = 0
     while reps < 3 or (time.perf_counter() - t0 < 2.0 and reps < 50):
-        c_oracle.occu_logp_grad(th, X, W, y)
+        run(th)
         reps += 1
     dt = time.perf_counter() - t0
     return {"value": sample * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample * reps} chain-evals of the full dataset ({X.shape[0]} sites), fp32 C/OpenMP "
+            "sample": f"{sample * reps} chain-evals of the full dataset ({X.shape[0]} sites), {arith} C/OpenMP "
                       f"restatement (oracle/occu_oracle.c), {threads} threads, {dt:.1f} s wall"}
 
 

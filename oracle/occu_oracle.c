@@ -142,3 +142,139 @@ int oracle_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * occu_cop (count detections, BASELINE config 4) -- restates
+ *   biolith/models/occu_cop.py:151-157   NaN mask + nan_to_num
+ *   biolith/models/occu_cop.py:160-171   rate_fp_constant / rate_fp_unoccupied ~ Exponential(1), sampled as
+ *                                        x = log(rate) (ExpTransform, log|J| = x)
+ *   biolith/models/occu_cop.py:222-255   psi, mu = exp(nu), rate = T (z mu + (1 - z) u + c), masked Poisson
+ *                                        log-prob (xlogy(y, rate) - lgamma(y + 1) - rate), enumeration over z
+ * in double arithmetic; `f32_clamps` selects numpyro's clamp_probs constants of the dtype the reference
+ * would run in (they only touch psi here).  Closed form and gradient: oracle/occupancy.py:occu_cop_logp_grad.
+ * theta = [beta | alpha | log c (if fpc) | log u (if fpu)].  Arrays: y (1,S,P,J), X (S,Ks), W (S,P,J,Ko),
+ * T (S,P,J) or NULL (ones), all double, C-contiguous.
+ * ---------------------------------------------------------------------------------------------- */
+static inline double n2n_clamped(double v, double rmax) { return isnan(v) ? 0.0 : (isinf(v) ? (v > 0 ? rmax : -rmax) : v); }
+
+int oracle_occu_cop_logp_grad(int f32_clamps, long S, int P, int J, int Ks, int Ko, const double* y, const double* X,
+                              const double* W, const double* T, const double* theta, int C, int fpc, int fpu,
+                              int prior, int nthreads, double* logp, double* grad) {
+  if (Ks > MAXK || Ko > MAXK) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  const double log_tiny = f32_clamps ? log((double)FLT_MIN) : log(DBL_MIN);
+  const double log_eps = f32_clamps ? log((double)FLT_EPSILON) : log(DBL_EPSILON);
+  const double log1m_eps = f32_clamps ? log1p(-(double)FLT_EPSILON) : log1p(-DBL_EPSILON);
+  const double neg_tiny = f32_clamps ? log1p(-(double)FLT_MIN) : log1p(-DBL_MIN);
+  const double rmax = f32_clamps ? (double)FLT_MAX : DBL_MAX;
+  const int D = Ks + Ko + 2 + (fpc != 0) + (fpu != 0);
+  const long U = S * (long)P;
+  for (int ci = 0; ci < C; ++ci) {
+    const double* th = theta + (size_t)ci * D;
+    const double* b = th;
+    const double* a = th + Ks + 1;
+    int ie = Ks + Ko + 2;
+    const double xc = fpc ? th[ie++] : 0.0, xu = fpu ? th[ie++] : 0.0;
+    const double c = fpc ? exp(xc) : 0.0, u = fpu ? exp(xu) : 0.0;
+    const double rho0 = u + c;
+    double acc[2 * MAXK + 5];
+    memset(acc, 0, sizeof(acc));
+    const int NQ = D + 1;
+#pragma omp parallel
+    {
+      double loc[2 * MAXK + 5];
+      memset(loc, 0, sizeof(loc));
+#pragma omp for schedule(static)
+      for (long un = 0; un < U; ++un) {
+        const long s = un / P;
+        int site_nan = 0;
+        double x[MAXK], eta = b[0];
+        for (int k = 0; k < Ks; ++k) {
+          const double v = X[s * Ks + k];
+          site_nan |= isnan(v);
+          x[k] = n2n_clamped(v, rmax);
+          eta += x[k] * b[k + 1];
+        }
+        double t1 = 0, t0 = 0, s1 = 0, s0 = 0, ga[MAXK + 1];
+        int b_is_neginf = 0;
+        for (int k = 0; k <= Ko; ++k) ga[k] = 0;
+        for (int j = 0; j < J; ++j) {
+          const double* w = W + ((size_t)un * J + j) * Ko;
+          double wv[MAXK], nu = a[0];
+          int cov_nan = site_nan;
+          for (int k = 0; k < Ko; ++k) {
+            cov_nan |= isnan(w[k]);
+            wv[k] = n2n_clamped(w[k], rmax);
+            nu += wv[k] * a[k + 1];
+          }
+          const double yv = y[(size_t)un * J + j];
+          if (cov_nan || !isfinite(yv)) continue; /* mask_missing_obs */
+          const double tv = T ? T[(size_t)un * J + j] : 1.0;
+          const double mu = exp(nu), rho1 = mu + c, lg = lgamma(yv + 1.0);
+          t1 += (yv > 0 ? yv * log(tv * rho1) : 0.0) - lg - tv * rho1;
+          if (yv > 0 && !(tv * rho0 > 0)) b_is_neginf = 1; /* xlogy(y, 0) = -inf */
+          else t0 += (yv > 0 ? yv * log(tv * rho0) : 0.0) - lg - tv * rho0;
+          const double d1 = (yv > 0 ? yv / rho1 : 0.0) - tv;
+          const double d0 = ((yv > 0 && rho0 > 0) ? yv / rho0 : 0.0) - tv;
+          s1 += d1;
+          s0 += d0;
+          const double g = d1 * mu;
+          ga[0] += g;
+          for (int k = 0; k < Ko; ++k) ga[k + 1] += g * wv[k];
+        }
+        /* clamped log psi / log(1 - psi), decisions in log space */
+        const double te = exp(-fabs(eta)), le = log1p(te), inv = 1.0 / (1.0 + te);
+        const double psi = eta >= 0 ? inv : te * inv;
+        const double lp0 = (eta < 0 ? eta : 0) - le, l10 = -(eta > 0 ? eta : 0) - le;
+        const int lo = lp0 <= log_tiny, hi = l10 <= log_eps, in_psi = !(lo || hi);
+        const double lpsi = lo ? log_tiny : (hi ? log1m_eps : lp0);
+        const double l1psi = lo ? neg_tiny : (hi ? log_eps : l10);
+        const double av = lpsi + t1;
+        double ell, r;
+        if (b_is_neginf) {
+          ell = av;
+          r = 1.0;
+        } else {
+          const double bv = l1psi + t0, dd = av - bv, td = exp(-fabs(dd)), iv = 1.0 / (1.0 + td);
+          r = dd >= 0 ? iv : td * iv;
+          ell = (av > bv ? av : bv) + log1p(td);
+        }
+        const double geta = in_psi ? r - psi : 0.0;
+        const double w0 = r < 1.0 ? (1.0 - r) * s0 : 0.0;
+        loc[0] += ell;
+        loc[1] += geta;
+        for (int k = 0; k < Ks; ++k) loc[2 + k] += geta * x[k];
+        for (int k = 0; k <= Ko; ++k) loc[2 + Ks + k] += r * ga[k];
+        int q = 3 + Ks + Ko;
+        if (fpc) loc[q++] += r * s1 + w0;
+        if (fpu) loc[q++] += w0;
+      }
+#pragma omp critical
+      for (int i = 0; i < NQ; ++i) acc[i] += loc[i];
+    }
+    double lp = acc[0];
+    for (int i = 0; i < Ks + Ko + 2; ++i) {
+      double g = acc[1 + i];
+      if (prior) {
+        lp += -0.5 * th[i] * th[i] - 0.91893853320467274178;
+        g -= th[i];
+      }
+      grad[(size_t)ci * D + i] = g;
+    }
+    int q = Ks + Ko + 2;
+    if (fpc) {
+      if (prior) lp += -c + xc; /* Exponential(1) on c, + log|dc/dx| */
+      grad[(size_t)ci * D + q] = acc[1 + q] * c + (prior ? 1.0 - c : 0.0);
+      ++q;
+    }
+    if (fpu) {
+      if (prior) lp += -u + xu;
+      grad[(size_t)ci * D + q] = acc[1 + q] * u + (prior ? 1.0 - u : 0.0);
+      ++q;
+    }
+    logp[ci] = lp;
+  }
+  return 0;
+}

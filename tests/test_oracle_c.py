@@ -22,3 +22,22 @@ def test_c_oracle_matches_numpy_oracle(name):
     lp1, _ = c_oracle.occu_logp_grad(g["thetas"], d["site_covs"], d["obs_covs"], d["obs"], dtype=np.float64,
                                      nthreads=1)
     np.testing.assert_allclose(lp1, lp * 0 + g["logp_f64"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["cop_default", "cop_missing_5x3", "cop_both_fp"])
+def test_c_cop_oracle_matches_numpy_oracle(name):
+    """The C restatement of occu_cop (BASELINE config 4; double arithmetic, clamp constants per dtype) is a
+    third independent derivation next to the enumerated and the closed-form numpy ones."""
+    from oracle import c_oracle
+
+    g = load_golden(name)
+    d, mk = g["data"], g["model_kwargs"]
+    kw = dict(fp_constant=mk.get("fp_constant", False), fp_unoccupied=mk.get("fp_unoccupied", False))
+    for mode, dt in (("f64", np.float64), ("f32", np.float32)):
+        for prior, lk, gk in ((True, "logp", "grad"), (False, "loglik", "gradlik")):
+            lp, gr = c_oracle.occu_cop_logp_grad(g["thetas"], d["site_covs"], d["obs_covs"], d["obs"],
+                                                 d.get("session_duration"), dtype=dt, prior=prior, **kw)
+            ref_lp, ref_gr = g[f"{lk}_{mode}"], g[f"{gk}_{mode}"]
+            np.testing.assert_allclose(lp, ref_lp, rtol=1e-12)
+            scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
+            assert (np.abs(gr - ref_gr) / scale).max() < 1e-11
