@@ -364,7 +364,7 @@ def main():
             line["exchange_check"] = exchange_check
         if nuts is not None:
             line["nuts"] = nuts
-        if not args.no_cpu_baseline and world == 1 and model in ("occu", "occu_cop"):
+        if not args.no_cpu_baseline and world == 1 and model in ("occu", "occu_cop", "occu_rn"):
             line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains, model, make_data.session_duration)
         print(json.dumps(_finite(line)), flush=True)
     lk.close()
@@ -452,6 +452,10 @@ def cpu_baseline(X, W, y, D, sample, model="occu", T=None):
     if model == "occu_cop":  # config 4: the C restatement computes in double (clamp constants of fp32)
         def run(t):
             return c_oracle.occu_cop_logp_grad(t, X, W, y, T, fp_constant=True)
+        arith = "fp64-arithmetic"
+    elif model == "occu_rn":  # config 3
+        def run(t):
+            return c_oracle.occu_rn_logp_grad(t, X, W, y, **MODEL_KW["occu_rn"])
         arith = "fp64-arithmetic"
     else:
         def run(t):

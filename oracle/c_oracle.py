@@ -28,6 +28,10 @@ def load(build_if_missing=True):
         _lib.oracle_occu_cop_logp_grad.argtypes = [
             C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oracle_occu_rn_logp_grad.restype = C.c_int
+        _lib.oracle_occu_rn_logp_grad.argtypes = [
+            C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -76,5 +80,27 @@ def occu_cop_logp_grad(theta, site_covs, obs_covs, obs, session_duration=None, d
                                        W.ctypes.data, None if T is None else T.ctypes.data, th.ctypes.data, n,
                                        int(bool(fp_constant)), int(bool(fp_unoccupied)), int(prior), int(nthreads),
                                        logp.ctypes.data, grad.ctypes.data)
+    assert rc == 0
+    return logp, grad
+
+
+def occu_rn_logp_grad(theta, site_covs, obs_covs, obs, max_abundance=100, dtype=np.float32, prior=True,
+                      fp_constant=False, nthreads=0):
+    """occu_rn in double arithmetic with the clamp constants of ``dtype``.  Reference layout as above."""
+    lib = load()
+    X = np.ascontiguousarray(np.asarray(site_covs, dtype=dtype), dtype=np.float64)
+    W = np.ascontiguousarray(np.asarray(obs_covs, dtype=dtype), dtype=np.float64)
+    y = np.ascontiguousarray(np.asarray(obs, dtype=dtype), dtype=np.float64)
+    th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    S, P, J, Ko = W.shape
+    Ks = X.shape[1]
+    D = Ks + Ko + 2 + int(bool(fp_constant))
+    assert y.shape == (1, S, P, J) and th.shape[1] == D
+    n = th.shape[0]
+    logp = np.empty(n)
+    grad = np.empty((n, D))
+    rc = lib.oracle_occu_rn_logp_grad(int(dtype == np.float32), S, P, J, Ks, Ko, int(max_abundance), y.ctypes.data,
+                                      X.ctypes.data, W.ctypes.data, th.ctypes.data, n, int(bool(fp_constant)),
+                                      int(prior), int(nthreads), logp.ctypes.data, grad.ctypes.data)
     assert rc == 0
     return logp, grad

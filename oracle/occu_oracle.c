@@ -164,10 +164,11 @@ int oracle_occu_cop_logp_grad(int f32_clamps, long S, int P, int J, int Ks, int 
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-  const double log_tiny = f32_clamps ? log((double)FLT_MIN) : log(DBL_MIN);
-  const double log_eps = f32_clamps ? log((double)FLT_EPSILON) : log(DBL_EPSILON);
-  const double log1m_eps = f32_clamps ? log1p(-(double)FLT_EPSILON) : log1p(-DBL_EPSILON);
-  const double neg_tiny = f32_clamps ? log1p(-(double)FLT_MIN) : log1p(-DBL_MIN);
+  /* an fp32 run holds the logs of the clamp constants in fp32 (as the numpy oracle and the kernels do) */
+  const double log_tiny = f32_clamps ? (double)logf(FLT_MIN) : log(DBL_MIN);
+  const double log_eps = f32_clamps ? (double)logf(FLT_EPSILON) : log(DBL_EPSILON);
+  const double log1m_eps = f32_clamps ? (double)log1pf(-FLT_EPSILON) : log1p(-DBL_EPSILON);
+  const double neg_tiny = f32_clamps ? (double)log1pf(-FLT_MIN) : log1p(-DBL_MIN);
   const double rmax = f32_clamps ? (double)FLT_MAX : DBL_MAX;
   const int D = Ks + Ko + 2 + (fpc != 0) + (fpu != 0);
   const long U = S * (long)P;
@@ -277,4 +278,171 @@ int oracle_occu_cop_logp_grad(int f32_clamps, long S, int P, int J, int Ks, int 
     logp[ci] = lp;
   }
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * occu_rn (Royle-Nichols, BASELINE config 3) -- restates
+ *   biolith/models/occu_rn.py:124-130    NaN mask + nan_to_num
+ *   biolith/models/occu_rn.py:139-143    prob_fp_constant ~ Beta(2, 5), sampled as x = logit(c)
+ *   biolith/models/occu_rn.py:188-194 + utils/distributions.py:31-40
+ *                                        lambda = exp(eta); N ~ Categorical(logits_k = k log lambda - lambda -
+ *                                        lgamma(k + 1), k = 0..K), normalised
+ *   biolith/models/occu_rn.py:205-222    r = sigmoid(nu); p_k = 1 - (1 - r)^k; Bernoulli(1 - (1 - p_k)(1 - c)),
+ *                                        masked, clamp_probs(tiny, 1 - eps); enumeration over N
+ * in double arithmetic with log(1 - P_kj) = k log(1 - r_j) + log(1 - c) carried in log space (the closed
+ * form of oracle/occupancy.py:occu_rn_logp_grad; see DESIGN.md section 2 for why not 1 - (1 - r)**N).
+ * theta = [beta | alpha | logit c (if fpc)].  Arrays double, reference layout.
+ * ---------------------------------------------------------------------------------------------- */
+int oracle_occu_rn_logp_grad(int f32_clamps, long S, int P, int J, int Ks, int Ko, int K, const double* y,
+                             const double* X, const double* W, const double* theta, int C, int fpc, int prior,
+                             int nthreads, double* logp, double* grad) {
+  if (Ks > MAXK || Ko > MAXK || K < 1 || K > 4096 || J > 4096) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  const double tiny = f32_clamps ? (double)FLT_MIN : DBL_MIN;
+  const double eps = f32_clamps ? (double)FLT_EPSILON : DBL_EPSILON;
+  /* an fp32 run holds the logs of the clamp constants in fp32 (as the numpy oracle and the kernels do) */
+  const double log_tiny = f32_clamps ? (double)logf(FLT_MIN) : log(tiny);
+  const double log_eps = f32_clamps ? (double)logf(FLT_EPSILON) : log(eps);
+  const double log1m_eps = f32_clamps ? (double)log1pf(-FLT_EPSILON) : log1p(-eps);
+  const double neg_tiny = f32_clamps ? (double)log1pf(-FLT_MIN) : log1p(-tiny);
+  const double rmax = f32_clamps ? (double)FLT_MAX : DBL_MAX;
+  const int D = Ks + Ko + 2 + (fpc != 0);
+  const long U = S * (long)P;
+  double* lgk = (double*)malloc((size_t)(K + 1) * sizeof(double));
+  if (!lgk) return -2;
+  for (int k = 0; k <= K; ++k) lgk[k] = lgamma((double)k + 1.0);
+  int status = 0;
+  for (int ci = 0; ci < C; ++ci) {
+    const double* th = theta + (size_t)ci * D;
+    const double* b = th;
+    const double* a = th + Ks + 1;
+    const double xc = fpc ? th[Ks + Ko + 2] : 0.0;
+    const double c = fpc ? 1.0 / (1.0 + exp(-xc)) : 0.0;
+    const double l1mc = fpc ? log1p(-c) : 0.0;
+    double acc[2 * MAXK + 5];
+    memset(acc, 0, sizeof(acc));
+    const int NQ = D + 1;
+#pragma omp parallel
+    {
+      double loc[2 * MAXK + 5];
+      memset(loc, 0, sizeof(loc));
+      double* A = (double*)malloc((size_t)(K + 1) * 2 * sizeof(double));   /* A_k, then w_k; log pi_k */
+      double* vis = (double*)malloc((size_t)J * (4 + MAXK) * sizeof(double)); /* per visit: m, y, r, u, W */
+      if (!A || !vis) {
+#pragma omp atomic write
+        status = -2;
+      }
+      double* lpi = A ? A + (K + 1) : NULL;
+#pragma omp for schedule(static)
+      for (long un = 0; un < U; ++un) {
+        if (!A || !vis) continue;
+        const long s = un / P;
+        int site_nan = 0;
+        double x[MAXK], eta = b[0];
+        for (int k = 0; k < Ks; ++k) {
+          const double v = X[s * Ks + k];
+          site_nan |= isnan(v);
+          x[k] = n2n_clamped(v, rmax);
+          eta += x[k] * b[k + 1];
+        }
+        const double lam = exp(eta);
+        /* normalised truncated-Poisson log-weights */
+        double mx = -INFINITY;
+        for (int k = 0; k <= K; ++k) {
+          lpi[k] = (k > 0 ? (double)k * eta : 0.0) - lgk[k] - lam; /* xlogy(k, lam) = k log lam = k eta */
+          if (lpi[k] > mx) mx = lpi[k];
+        }
+        double z = 0;
+        for (int k = 0; k <= K; ++k) z += exp(lpi[k] - mx);
+        const double lse = mx + log(z);
+        double Epi = 0;
+        for (int k = 0; k <= K; ++k) {
+          lpi[k] -= lse;
+          Epi += (double)k * exp(lpi[k]);
+          A[k] = lpi[k];
+        }
+        for (int j = 0; j < J; ++j) {
+          double* v = vis + (size_t)j * (4 + MAXK);
+          const double* w = W + ((size_t)un * J + j) * Ko;
+          double nu = a[0];
+          int cov_nan = site_nan;
+          for (int k = 0; k < Ko; ++k) {
+            cov_nan |= isnan(w[k]);
+            v[4 + k] = n2n_clamped(w[k], rmax);
+            nu += v[4 + k] * a[k + 1];
+          }
+          const double yv = y[(size_t)un * J + j];
+          v[0] = (cov_nan || !isfinite(yv)) ? 0.0 : 1.0;
+          v[1] = yv;
+          const double t = exp(-fabs(nu)), inv = 1.0 / (1.0 + t);
+          v[2] = nu >= 0 ? inv : t * inv;                 /* r */
+          v[3] = -(nu > 0 ? nu : 0) - log1p(t);           /* log(1 - r) */
+          if (v[0] == 0.0) continue;
+          for (int k = 0; k <= K; ++k) {
+            const double lq = (double)k * v[3] + l1mc, Pk = -expm1(lq);
+            const int inr = (lq > log_eps) && (Pk > tiny);
+            if (yv > 0.5) A[k] += inr ? log(Pk) : (Pk <= tiny ? log_tiny : log1m_eps);
+            else A[k] += inr ? lq : (Pk <= tiny ? neg_tiny : log_eps);
+          }
+        }
+        mx = -INFINITY;
+        for (int k = 0; k <= K; ++k) if (A[k] > mx) mx = A[k];
+        z = 0;
+        for (int k = 0; k <= K; ++k) z += exp(A[k] - mx);
+        const double ell = mx + log(z);
+        double Ew = 0;
+        for (int k = 0; k <= K; ++k) {
+          A[k] = exp(A[k] - ell); /* posterior weight of N = k */
+          Ew += (double)k * A[k];
+        }
+        const double geta = Ew - Epi;
+        double ga[MAXK + 1], gc = 0;
+        for (int k = 0; k <= Ko; ++k) ga[k] = 0;
+        for (int j = 0; j < J; ++j) {
+          const double* v = vis + (size_t)j * (4 + MAXK);
+          if (v[0] == 0.0) continue;
+          double dnu = 0;
+          for (int k = 0; k <= K; ++k) {
+            const double lq = (double)k * v[3] + l1mc, Pk = -expm1(lq);
+            const int inr = (lq > log_eps) && (Pk > tiny);
+            const double dt = inr ? (v[1] > 0.5 ? -exp(lq) / Pk : 1.0) : 0.0; /* dt / dlq */
+            dnu += A[k] * dt * (-(double)k * v[2]);
+            gc += A[k] * dt;
+          }
+          ga[0] += dnu;
+          for (int k = 0; k < Ko; ++k) ga[k + 1] += dnu * v[4 + k];
+        }
+        loc[0] += ell;
+        loc[1] += geta;
+        for (int k = 0; k < Ks; ++k) loc[2 + k] += geta * x[k];
+        for (int k = 0; k <= Ko; ++k) loc[2 + Ks + k] += ga[k];
+        if (fpc) loc[3 + Ks + Ko] += gc * (-1.0 / (1.0 - c));
+      }
+      free(A);
+      free(vis);
+#pragma omp critical
+      for (int i = 0; i < NQ; ++i) acc[i] += loc[i];
+    }
+    double lp = acc[0];
+    for (int i = 0; i < Ks + Ko + 2; ++i) {
+      double g = acc[1 + i];
+      if (prior) {
+        lp += -0.5 * th[i] * th[i] - 0.91893853320467274178;
+        g -= th[i];
+      }
+      grad[(size_t)ci * D + i] = g;
+    }
+    if (fpc) {
+      const int q = Ks + Ko + 2;
+      const double pa = 2.0, pb = 5.0;
+      const double lsc = -log1p(exp(-xc)) , ls1 = -log1p(exp(xc)); /* log c, log(1 - c) */
+      if (prior) lp += pa * lsc + pb * ls1 + lgamma(pa + pb) - lgamma(pa) - lgamma(pb);
+      grad[(size_t)ci * D + q] = acc[1 + q] * c * (1.0 - c) + (prior ? pa * (1.0 - c) - pb * c : 0.0);
+    }
+    logp[ci] = lp;
+  }
+  free(lgk);
+  return status;
 }

@@ -41,3 +41,38 @@ def test_c_cop_oracle_matches_numpy_oracle(name):
             np.testing.assert_allclose(lp, ref_lp, rtol=1e-12)
             scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
             assert (np.abs(gr - ref_gr) / scale).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", ["rn_default", "rn_5x3"])
+def test_c_rn_oracle_matches_numpy_oracle(name):
+    """C restatement of occu_rn (BASELINE config 3) against the numpy closed form on the goldens."""
+    from oracle import c_oracle
+
+    g = load_golden(name)
+    d, mk = g["data"], g["model_kwargs"]
+    for mode, dt in (("f64", np.float64), ("f32", np.float32)):
+        for prior, lk, gk in ((True, "logp", "grad"), (False, "loglik", "gradlik")):
+            lp, gr = c_oracle.occu_rn_logp_grad(g["thetas"], d["site_covs"], d["obs_covs"], d["obs"],
+                                                max_abundance=mk["max_abundance"], dtype=dt, prior=prior,
+                                                fp_constant=mk.get("fp_constant", False))
+            ref_lp, ref_gr = g[f"{lk}_{mode}"], g[f"{gk}_{mode}"]
+            np.testing.assert_allclose(lp, ref_lp, rtol=1e-11)
+            scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
+            assert (np.abs(gr - ref_gr) / scale).max() < 1e-10
+
+
+def test_c_rn_oracle_false_positive_constant():
+    from oracle import c_oracle
+    from oracle import occupancy as orc
+
+    g = load_golden("rn_5x3")
+    d = g["data"]
+    rng = np.random.default_rng(0)
+    th = np.concatenate([g["thetas"][:4], rng.uniform(-3, 0, size=(4, 1))], axis=1)
+    pr = orc.prepare(d["site_covs"], d["obs_covs"], d["obs"], dtype=np.float32)
+    ref_lp, ref_gr = orc.logp_grad("occu_rn", th, pr, max_abundance=30, fp_constant=True, dtype=np.float32)
+    lp, gr = c_oracle.occu_rn_logp_grad(th, d["site_covs"], d["obs_covs"], d["obs"], max_abundance=30,
+                                        fp_constant=True)
+    np.testing.assert_allclose(lp, ref_lp, rtol=1e-11)
+    scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
+    assert (np.abs(gr - ref_gr) / scale).max() < 1e-10
