@@ -330,7 +330,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "model": model, "strict_math": bool(args.strict_math), "sites": int(units_sites),
+            "config": {"workload": args.workload, "likelihood": model, "strict_math": bool(args.strict_math), "sites": int(units_sites),
                        "visits": int(W.shape[2]), "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]),
                        "chains_per_gpu": chains, "chains_total": chains_total, "sharding": shard,
                        "theta": "U(-2,2) per chain (init_to_uniform)" if args.theta == "uniform"
