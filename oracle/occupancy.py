@@ -201,7 +201,8 @@ def _linear(coef, covs_flat):
 
 def _flatten(covs):
     """modeling.py:22-28: (n_covs, *obs_shape) -> (n_obs, n_covs), obs_shape."""
-    return covs.reshape(covs.shape[0], -1).T, covs.shape[1:]
+    # (explicit size instead of -1 so that an intercept-only predictor, n_covs = 0, stays well defined)
+    return covs.reshape(covs.shape[0], int(np.prod(covs.shape[1:]))).T, covs.shape[1:]
 
 
 def _extras_prior_sigmoid(x, a=2.0, b=5.0):
