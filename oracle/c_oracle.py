@@ -32,6 +32,14 @@ def load(build_if_missing=True):
         _lib.oracle_occu_rn_logp_grad.argtypes = [
             C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oracle_nmixture_logp_grad.restype = C.c_int
+        _lib.oracle_nmixture_logp_grad.argtypes = [
+            C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _lib.oracle_occu_cs_logp_grad.restype = C.c_int
+        _lib.oracle_occu_cs_logp_grad.argtypes = [
+            C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -102,5 +110,47 @@ def occu_rn_logp_grad(theta, site_covs, obs_covs, obs, max_abundance=100, dtype=
     rc = lib.oracle_occu_rn_logp_grad(int(dtype == np.float32), S, P, J, Ks, Ko, int(max_abundance), y.ctypes.data,
                                       X.ctypes.data, W.ctypes.data, th.ctypes.data, n, int(bool(fp_constant)),
                                       int(prior), int(nthreads), logp.ctypes.data, grad.ctypes.data)
+    assert rc == 0
+    return logp, grad
+
+
+def nmixture_logp_grad(theta, site_covs, obs_covs, obs, max_abundance=100, dtype=np.float32, prior=True, nthreads=0):
+    """nmixture in double arithmetic (arrays first rounded to ``dtype``).  Reference layout as above."""
+    lib = load()
+    X = np.ascontiguousarray(np.asarray(site_covs, dtype=dtype), dtype=np.float64)
+    W = np.ascontiguousarray(np.asarray(obs_covs, dtype=dtype), dtype=np.float64)
+    y = np.ascontiguousarray(np.asarray(obs, dtype=dtype), dtype=np.float64)
+    th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    S, P, J, Ko = W.shape
+    Ks = X.shape[1]
+    assert y.shape == (1, S, P, J) and th.shape[1] == Ks + Ko + 2
+    n = th.shape[0]
+    logp = np.empty(n)
+    grad = np.empty((n, th.shape[1]))
+    rc = lib.oracle_nmixture_logp_grad(int(dtype == np.float32), S, P, J, Ks, Ko, int(max_abundance), y.ctypes.data,
+                                       X.ctypes.data, W.ctypes.data, th.ctypes.data, n, int(prior), int(nthreads),
+                                       logp.ctypes.data, grad.ctypes.data)
+    assert rc == 0
+    return logp, grad
+
+
+def occu_cs_logp_grad(theta, site_covs, obs_covs, obs, dtype=np.float32, prior=True, prior_mu_scale=10.0,
+                      prior_sigma=(5.0, 1.0), nthreads=0):
+    """occu_cs in double arithmetic with the clamp constants of ``dtype``.  Reference layout as above."""
+    lib = load()
+    X = np.ascontiguousarray(np.asarray(site_covs, dtype=dtype), dtype=np.float64)
+    W = np.ascontiguousarray(np.asarray(obs_covs, dtype=dtype), dtype=np.float64)
+    y = np.ascontiguousarray(np.asarray(obs, dtype=dtype), dtype=np.float64)
+    th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    S, P, J, Ko = W.shape
+    Ks = X.shape[1]
+    assert y.shape == (1, S, P, J) and th.shape[1] == Ks + Ko + 6
+    n = th.shape[0]
+    logp = np.empty(n)
+    grad = np.empty((n, th.shape[1]))
+    rc = lib.oracle_occu_cs_logp_grad(int(dtype == np.float32), S, P, J, Ks, Ko, y.ctypes.data, X.ctypes.data,
+                                      W.ctypes.data, th.ctypes.data, n, int(prior), float(prior_mu_scale),
+                                      float(prior_sigma[0]), float(prior_sigma[1]), int(nthreads), logp.ctypes.data,
+                                      grad.ctypes.data)
     assert rc == 0
     return logp, grad

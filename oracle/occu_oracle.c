@@ -6,6 +6,9 @@
  * PARITY STATUS: unpinned against numpyro (see oracle/occupancy.py header); this file is pinned
  * to oracle/occupancy.py (tests/test_oracle_c.py) which is pinned to the golden fixtures.
  *
+ * Five entry points, one per model (occu below; occu_cop, occu_rn, nmixture, occu_cs further down, each
+ * with its own header citing the reference lines it follows).
+ *
  * Restates, for the `occu` model without false positives (the BASELINE.json metric config):
  *   biolith/models/occu.py:136-142   NaN mask + nan_to_num            (done on the fly per visit)
  *   biolith/regression/linear.py:59-66  eta = b0 + X.b, nu = a0 + W.a
@@ -445,4 +448,253 @@ int oracle_occu_rn_logp_grad(int f32_clamps, long S, int P, int J, int Ks, int K
   }
   free(lgk);
   return status;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * nmixture (Royle 2004) -- restates biolith/models/nmixture.py:124-220: lambda = exp(eta);
+ * N in {max_j y_j .. K} with truncated, un-renormalised Poisson weights (the Categorical normaliser and the
+ * numpyro.factor cancel); y_j ~ Binomial(N, sigmoid(nu_j)), NaN-masked.  Double arithmetic, no clamps in this
+ * model.  Closed form: oracle/occupancy.py:nmixture_logp_grad.  theta = [beta | alpha].
+ * ---------------------------------------------------------------------------------------------- */
+int oracle_nmixture_logp_grad(int f32_data, long S, int P, int J, int Ks, int Ko, int K, const double* y,
+                              const double* X, const double* W, const double* theta, int C, int prior,
+                              int nthreads, double* logp, double* grad) {
+  if (Ks > MAXK || Ko > MAXK || K < 1 || K > 4096 || J > 4096) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  const double rmax = f32_data ? (double)FLT_MAX : DBL_MAX;
+  const int D = Ks + Ko + 2, NQ = D + 1;
+  const long U = S * (long)P;
+  double* lgk = (double*)malloc((size_t)(K + 1) * sizeof(double));
+  if (!lgk) return -2;
+  for (int k = 0; k <= K; ++k) lgk[k] = lgamma((double)k + 1.0);
+  int status = 0;
+  for (int ci = 0; ci < C; ++ci) {
+    const double* th = theta + (size_t)ci * D;
+    const double* b = th;
+    const double* a = th + Ks + 1;
+    double acc[2 * MAXK + 5];
+    memset(acc, 0, sizeof(acc));
+#pragma omp parallel
+    {
+      double loc[2 * MAXK + 5];
+      memset(loc, 0, sizeof(loc));
+      double* A = (double*)malloc((size_t)(K + 1) * sizeof(double));
+      double* vis = (double*)malloc((size_t)J * (3 + MAXK) * sizeof(double)); /* per visit: m, y, p, W */
+      if (!A || !vis) {
+#pragma omp atomic write
+        status = -2;
+      }
+#pragma omp for schedule(static)
+      for (long un = 0; un < U; ++un) {
+        if (!A || !vis) continue;
+        const long s = un / P;
+        int site_nan = 0;
+        double x[MAXK], eta = b[0];
+        for (int k = 0; k < Ks; ++k) {
+          const double v = X[s * Ks + k];
+          site_nan |= isnan(v);
+          x[k] = n2n_clamped(v, rmax);
+          eta += x[k] * b[k + 1];
+        }
+        const double lam = exp(eta);
+        double Usum = 0, V = 0;
+        int kmin = 0;
+        for (int j = 0; j < J; ++j) {
+          double* v = vis + (size_t)j * (3 + MAXK);
+          const double* w = W + ((size_t)un * J + j) * Ko;
+          double nu = a[0];
+          int cov_nan = site_nan;
+          for (int k = 0; k < Ko; ++k) {
+            cov_nan |= isnan(w[k]);
+            v[3 + k] = n2n_clamped(w[k], rmax);
+            nu += v[3 + k] * a[k + 1];
+          }
+          const double yv = y[(size_t)un * J + j];
+          v[0] = (cov_nan || !isfinite(yv)) ? 0.0 : 1.0;
+          v[1] = yv;
+          const double t = exp(-fabs(nu)), inv = 1.0 / (1.0 + t);
+          v[2] = nu >= 0 ? inv : t * inv; /* p */
+          if (v[0] == 0.0) continue;
+          Usum += -(nu > 0 ? nu : 0) - log1p(t); /* log(1 - p) */
+          V += yv * nu;
+          if ((int)yv > kmin) kmin = (int)yv;
+        }
+        double mx = -INFINITY;
+        for (int k = kmin; k <= K; ++k) {
+          double ck = -lgk[k];
+          for (int j = 0; j < J; ++j) {
+            const double* v = vis + (size_t)j * (3 + MAXK);
+            if (v[0] != 0.0) ck += lgk[k] - lgk[(int)v[1]] - lgk[k - (int)v[1]];
+          }
+          A[k] = (double)k * (eta + Usum) - lam + ck;
+          if (A[k] > mx) mx = A[k];
+        }
+        double z = 0, Ek = 0;
+        for (int k = kmin; k <= K; ++k) {
+          const double e = exp(A[k] - mx);
+          z += e;
+          Ek += (double)k * e;
+        }
+        Ek /= z;
+        const double ell = V + mx + log(z), geta = Ek - lam;
+        loc[0] += ell;
+        loc[1] += geta;
+        for (int k = 0; k < Ks; ++k) loc[2 + k] += geta * x[k];
+        for (int j = 0; j < J; ++j) {
+          const double* v = vis + (size_t)j * (3 + MAXK);
+          if (v[0] == 0.0) continue;
+          const double dnu = v[1] - v[2] * Ek;
+          loc[2 + Ks] += dnu;
+          for (int k = 0; k < Ko; ++k) loc[3 + Ks + k] += dnu * v[3 + k];
+        }
+      }
+      free(A);
+      free(vis);
+#pragma omp critical
+      for (int i = 0; i < NQ; ++i) acc[i] += loc[i];
+    }
+    double lp = acc[0];
+    for (int i = 0; i < D; ++i) {
+      double g = acc[1 + i];
+      if (prior) {
+        lp += -0.5 * th[i] * th[i] - 0.91893853320467274178;
+        g -= th[i];
+      }
+      grad[(size_t)ci * D + i] = g;
+    }
+    logp[ci] = lp;
+  }
+  free(lgk);
+  return status;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * occu_cs (continuous-score occupancy) -- restates biolith/models/occu_cs.py:146-223:
+ * z ~ Bernoulli(psi~) and f_j ~ Bernoulli(clamp(z sigmoid(nu_j))) enumerated, s_j ~ Normal((1-f) mu0 + f mu1,
+ * (1-f) sigma0 + f sigma1) NaN-masked; extras in unconstrained space [mu0, log(mu1 - mu0), log sigma0,
+ * log sigma1] with Normal(0, s) / left-truncated Normal(0, s) / Gamma(a, b) priors and their log-Jacobians.
+ * Double arithmetic, clamp constants of either dtype.  Closed form: oracle/occupancy.py:occu_cs_logp_grad.
+ * ---------------------------------------------------------------------------------------------- */
+static inline double softplus_d(double x) { return (x > 0 ? x : 0) + log1p(exp(-fabs(x))); }
+static inline double sigmoid_d(double x) { const double t = exp(-fabs(x)), inv = 1.0 / (1.0 + t); return x >= 0 ? inv : t * inv; }
+
+int oracle_occu_cs_logp_grad(int f32_clamps, long S, int P, int J, int Ks, int Ko, const double* y, const double* X,
+                             const double* W, const double* theta, int C, int prior, double prior_mu_scale,
+                             double prior_sigma_a, double prior_sigma_b, int nthreads, double* logp, double* grad) {
+  if (Ks > MAXK || Ko > MAXK) return -1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  const double log_tiny = f32_clamps ? (double)logf(FLT_MIN) : log(DBL_MIN);
+  const double log_eps = f32_clamps ? (double)logf(FLT_EPSILON) : log(DBL_EPSILON);
+  const double log1m_eps = f32_clamps ? (double)log1pf(-FLT_EPSILON) : log1p(-DBL_EPSILON);
+  const double neg_tiny = f32_clamps ? (double)log1pf(-FLT_MIN) : log1p(-DBL_MIN);
+  const double rmax = f32_clamps ? (double)FLT_MAX : DBL_MAX;
+  const double h2pi = 0.91893853320467274178;
+  const int D = Ks + Ko + 6, NQ = D + 1, i0 = Ks + Ko + 2;
+  const long U = S * (long)P;
+  for (int ci = 0; ci < C; ++ci) {
+    const double* th = theta + (size_t)ci * D;
+    const double* b = th;
+    const double* a = th + Ks + 1;
+    const double mu0 = th[i0], e1x = exp(th[i0 + 1]), mu1 = mu0 + e1x, xs0 = th[i0 + 2], xs1 = th[i0 + 3];
+    const double sg0 = exp(xs0), sg1 = exp(xs1);
+    double acc[2 * MAXK + 8];
+    memset(acc, 0, sizeof(acc));
+#pragma omp parallel
+    {
+      double loc[2 * MAXK + 8];
+      memset(loc, 0, sizeof(loc));
+#pragma omp for schedule(static)
+      for (long un = 0; un < U; ++un) {
+        const long s = un / P;
+        int site_nan = 0;
+        double x[MAXK], eta = b[0];
+        for (int k = 0; k < Ks; ++k) {
+          const double v = X[s * Ks + k];
+          site_nan |= isnan(v);
+          x[k] = n2n_clamped(v, rmax);
+          eta += x[k] * b[k + 1];
+        }
+        double L1 = 0, L0 = 0, ga[MAXK + 1];
+        double Ae0 = 0, Aq0 = 0, Ae1 = 0, Aq1 = 0, Be0 = 0, Bq0 = 0, Be1 = 0, Bq1 = 0;
+        for (int k = 0; k <= Ko; ++k) ga[k] = 0;
+        for (int j = 0; j < J; ++j) {
+          const double* w = W + ((size_t)un * J + j) * Ko;
+          double wv[MAXK], nu = a[0];
+          int cov_nan = site_nan;
+          for (int k = 0; k < Ko; ++k) {
+            cov_nan |= isnan(w[k]);
+            wv[k] = n2n_clamped(w[k], rmax);
+            nu += wv[k] * a[k + 1];
+          }
+          const double sc = y[(size_t)un * J + j];
+          if (cov_nan || !isfinite(sc)) continue; /* mask_missing_obs */
+          const double e0 = (sc - mu0) / sg0, e1 = (sc - mu1) / sg1;
+          const double n0 = -0.5 * e0 * e0 - xs0 - h2pi, n1 = -0.5 * e1 * e1 - xs1 - h2pi;
+          /* clamped log q~, log(1 - q~) of q = sigmoid(nu) */
+          const double pj = sigmoid_d(nu), lq0 = -softplus_d(-nu), l1q0 = -softplus_d(nu);
+          const int lo = lq0 <= log_tiny, hi = l1q0 <= log_eps, inr = !(lo || hi);
+          const double lq = lo ? log_tiny : (hi ? log1m_eps : lq0), l1q = lo ? neg_tiny : (hi ? log_eps : l1q0);
+          const double a0 = l1q + n0, a1 = lq + n1;           /* z = 1 */
+          const double c0 = neg_tiny + n0, c1 = log_tiny + n1; /* z = 0: q~ = tiny */
+          L1 += a0 + softplus_d(a1 - a0);
+          L0 += c0 + softplus_d(c1 - c0);
+          const double w1 = sigmoid_d(a1 - a0), v1 = sigmoid_d(c1 - c0);
+          const double g = inr ? w1 - pj : 0.0;
+          ga[0] += g;
+          for (int k = 0; k < Ko; ++k) ga[k + 1] += g * wv[k];
+          const double q0 = e0 * e0 - 1.0, q1 = e1 * e1 - 1.0;
+          Ae0 += (1 - w1) * e0; Aq0 += (1 - w1) * q0; Ae1 += w1 * e1; Aq1 += w1 * q1;
+          Be0 += (1 - v1) * e0; Bq0 += (1 - v1) * q0; Be1 += v1 * e1; Bq1 += v1 * q1;
+        }
+        const double psi = sigmoid_d(eta), lp0 = -softplus_d(-eta), l10 = -softplus_d(eta);
+        const int lo = lp0 <= log_tiny, hi = l10 <= log_eps, in_psi = !(lo || hi);
+        const double lpsi = lo ? log_tiny : (hi ? log1m_eps : lp0), l1psi = lo ? neg_tiny : (hi ? log_eps : l10);
+        const double av = lpsi + L1, bv = l1psi + L0;
+        const double ell = bv + softplus_d(av - bv), r = sigmoid_d(av - bv);
+        const double geta = in_psi ? r - psi : 0.0;
+        loc[0] += ell;
+        loc[1] += geta;
+        for (int k = 0; k < Ks; ++k) loc[2 + k] += geta * x[k];
+        for (int k = 0; k <= Ko; ++k) loc[2 + Ks + k] += r * ga[k];
+        const double g_mu0 = (r * Ae0 + (1 - r) * Be0) / sg0, g_mu1 = (r * Ae1 + (1 - r) * Be1) / sg1;
+        loc[1 + i0] += g_mu0 + g_mu1; /* mu1 = mu0 + exp(x1) */
+        loc[2 + i0] += g_mu1 * e1x;
+        loc[3 + i0] += r * Aq0 + (1 - r) * Bq0;
+        loc[4 + i0] += r * Aq1 + (1 - r) * Bq1;
+      }
+#pragma omp critical
+      for (int i = 0; i < NQ; ++i) acc[i] += loc[i];
+    }
+    double lp = acc[0];
+    for (int i = 0; i < i0; ++i) {
+      double g = acc[1 + i];
+      if (prior) {
+        lp += -0.5 * th[i] * th[i] - h2pi;
+        g -= th[i];
+      }
+      grad[(size_t)ci * D + i] = g;
+    }
+    double ge[4] = {acc[1 + i0], acc[2 + i0], acc[3 + i0], acc[4 + i0]};
+    if (prior) {
+      const double sm = prior_mu_scale, pa = prior_sigma_a, pb = prior_sigma_b, t = mu0 / sm;
+      const double sf = 0.5 * erfc(t * 0.70710678118654752440); /* 1 - Phi(t) */
+      const double hazard = exp(-0.5 * t * t - h2pi) / sf;
+      lp += -0.5 * t * t - log(sm) - h2pi;
+      lp += -0.5 * (mu1 / sm) * (mu1 / sm) - log(sm) - h2pi - log(sf) + th[i0 + 1];
+      ge[0] += -mu0 / (sm * sm) - mu1 / (sm * sm) + hazard / sm;
+      ge[1] += -mu1 / (sm * sm) * e1x + 1.0;
+      for (int i = 0; i < 2; ++i) {
+        const double xs = th[i0 + 2 + i], sg = i ? sg1 : sg0;
+        lp += pa * log(pb) + (pa - 1.0) * xs - pb * sg - lgamma(pa) + xs;
+        ge[2 + i] += pa - pb * sg;
+      }
+    }
+    for (int i = 0; i < 4; ++i) grad[(size_t)ci * D + i0 + i] = ge[i];
+    logp[ci] = lp;
+  }
+  return 0;
 }

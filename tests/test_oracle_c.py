@@ -76,3 +76,35 @@ def test_c_rn_oracle_false_positive_constant():
     np.testing.assert_allclose(lp, ref_lp, rtol=1e-11)
     scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
     assert (np.abs(gr - ref_gr) / scale).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["nmix_default", "nmix_missing_5x3"])
+def test_c_nmixture_oracle_matches_numpy_oracle(name):
+    from oracle import c_oracle
+
+    g = load_golden(name)
+    d, mk = g["data"], g["model_kwargs"]
+    for mode, dt in (("f64", np.float64), ("f32", np.float32)):
+        for prior, lk, gk in ((True, "logp", "grad"), (False, "loglik", "gradlik")):
+            lp, gr = c_oracle.nmixture_logp_grad(g["thetas"], d["site_covs"], d["obs_covs"], d["obs"],
+                                                 max_abundance=mk["max_abundance"], dtype=dt, prior=prior)
+            ref_lp, ref_gr = g[f"{lk}_{mode}"], g[f"{gk}_{mode}"]
+            np.testing.assert_allclose(lp, ref_lp, rtol=1e-11)
+            scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
+            assert (np.abs(gr - ref_gr) / scale).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["cs_default", "cs_missing_5x3"])
+def test_c_occu_cs_oracle_matches_numpy_oracle(name):
+    from oracle import c_oracle
+
+    g = load_golden(name)
+    d = g["data"]
+    for mode, dt in (("f64", np.float64), ("f32", np.float32)):
+        for prior, lk, gk in ((True, "logp", "grad"), (False, "loglik", "gradlik")):
+            lp, gr = c_oracle.occu_cs_logp_grad(g["thetas"], d["site_covs"], d["obs_covs"], d["obs"], dtype=dt,
+                                                prior=prior)
+            ref_lp, ref_gr = g[f"{lk}_{mode}"], g[f"{gk}_{mode}"]
+            np.testing.assert_allclose(lp, ref_lp, rtol=1e-11)
+            scale = np.maximum(np.abs(ref_gr).max(axis=1, keepdims=True), 1.0)
+            assert (np.abs(gr - ref_gr) / scale).max() < 1e-10
