@@ -52,7 +52,7 @@ WORKLOADS = {
                                          deployment_days_per_site=70), 256, "chains"),
 }
 MODEL_KW = {"occu_rn": dict(max_abundance=50), "occu_cop": dict(false_positives_constant=True)}
-METRIC = "logp+grad evals/sec (occu, 1M sites x 8 visits, chain-batched)"
+METRIC = "logp+grad evals/sec (occu, 1M sites x 8 visits, chain-batched); NUTS ESS/sec of the same run under 'nuts'"
 UNIT = "chain-evals/s"
 
 
@@ -364,6 +364,19 @@ def main():
             line["exchange_check"] = exchange_check
         if nuts is not None:
             line["nuts"] = nuts
+        if world == 1 and model == "occu" and args.dtype == "float32" and not args.strict_math:
+            # the same evaluation with libm expf / log1pf / IEEE division (BL_FLAG_STRICT_MATH), for the record:
+            # the default kernels use bounded-error SFU forms (DESIGN.md "Numerics"); never fatal for the line
+            try:
+                with bb.OccupancyLikelihood(model, X, W, y, None, dtype=args.dtype, device=local_rank,
+                                            max_chains=chains, strict_math=True) as strict:
+                    strict.eval_timed(d_theta.ptr, chains, d_logp.ptr, d_grad.ptr, stream, iters=1)
+                    ms_s = min(strict.eval_timed(d_theta.ptr, chains, d_logp.ptr, d_grad.ptr, stream, iters=2)
+                               for _ in range(2))
+                line["strict_math"] = {"ms_per_step": ms_s, "value": chains / (ms_s * 1e-3), "unit": UNIT,
+                                       "note": "libm-accurate fp32 math in the site-parallel engine, same data and thetas"}
+            except Exception as exc:  # noqa: BLE001
+                line["strict_math"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline and world == 1 and model in ("occu", "occu_cop", "occu_rn"):
             line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains, model, make_data.session_duration)
         print(json.dumps(_finite(line)), flush=True)
