@@ -100,7 +100,7 @@ def make_loglik(likelihood: OccupancyLikelihood):
 def _drop_in(model_name):
     def model(site_covs, obs_covs, coords=None, ell=1.0, session_duration=None,
               false_positives_constant=False, false_positives_unoccupied=False, max_abundance=100, obs=None,
-              n_species=1, prior_beta=None, prior_alpha=None, **unsupported):
+              n_species=1, prior_beta=None, prior_alpha=None, prior_mu=None, prior_sigma=None, **unsupported):
         _require_jax()
         import numpyro
         import numpyro.distributions as dist
@@ -114,7 +114,17 @@ def _drop_in(model_name):
                            false_positives_unoccupied, max_abundance)
         loglik = make_loglik(lk)
         extras = []
-        if model_name == "occu_cop":
+        if model_name == "occu_cs":
+            # occu_cs.py:146-154, unchanged sample sites; the kernel takes the extras in numpyro's own
+            # unconstrained coordinates, so jax differentiates through these three elementary maps
+            pm = prior_mu if isinstance(prior_mu, tuple) else (prior_mu or dist.Normal(0, 10),) * 2
+            ps = prior_sigma if isinstance(prior_sigma, tuple) else (prior_sigma or dist.Gamma(5, 1),) * 2
+            mu0 = numpyro.sample("mu0", pm[0])
+            mu1 = numpyro.sample("mu1", dist.TruncatedDistribution(pm[1], low=mu0))
+            sigma0 = numpyro.sample("sigma0", ps[0])
+            sigma1 = numpyro.sample("sigma1", ps[1])
+            extras += [mu0, jnp.log(mu1 - mu0), jnp.log(sigma0), jnp.log(sigma1)]
+        elif model_name == "occu_cop":
             if false_positives_constant:
                 extras.append(jnp.log(numpyro.sample("rate_fp_constant", dist.Exponential())))
             if false_positives_unoccupied:
@@ -156,3 +166,4 @@ occu = _drop_in("occu")
 occu_rn = _drop_in("occu_rn")
 occu_cop = _drop_in("occu_cop")
 nmixture = _drop_in("nmixture")
+occu_cs = _drop_in("occu_cs")
