@@ -784,6 +784,133 @@ def occu_cs_logp_grad(theta, pr: Prepared, *, dtype=np.float32, prior=True, prio
     return logp, grad
 
 
+
+# ============================================================ random effects (groundwork)
+# SURVEY 8 row f4, third item: site / observation random effects of `occu` (occu.py:168-173, 191-196,
+# 215-228).  NOT on the accelerated path yet (biolith_b200.fit raises for them); restated here so that the
+# kernels of the next round have their checker.  theta layout (one chain, n_species = 1):
+#   [ beta | alpha | log site_re_sd (if site) | log obs_re_sd (if obs) | a_s (S) | d_s (S) | o_spj (S*P*J) ]
+# a = site_re_occ, d = site_re_det (both ~ Normal(0, site_re_sd), occu.py:191-193), o = obs_re ~ Normal(0,
+# obs_re_sd) for EVERY (s, p, j), masked or not (the plate is not under mask_missing_obs, occu.py:215-218);
+# the two scales ~ HalfNormal(1) in log space (ExpTransform, log|J| = x).
+def _half_normal_log(x, scale=1.0):
+    """HalfNormal(scale) on sd = exp(x) plus log|d sd/dx|; returns (sd, log-density, d/dx)."""
+    sd = np.exp(x)
+    lp = np.log(2.0) + normal_log_prob(sd, 0.0, scale) + x
+    return sd, lp, -(sd / scale) ** 2 + 1.0
+
+
+def occu_re_dims(S, P, J, Ks, Ko, site_re, obs_re):
+    n_sd = int(bool(site_re)) + int(bool(obs_re))
+    return Ks + Ko + 2 + n_sd + (2 * S if site_re else 0) + (S * P * J if obs_re else 0)
+
+
+def _split_re(theta, S, P, J, Ks, Ko, site_re, obs_re):
+    theta = np.asarray(theta, np.float64)
+    i = Ks + Ko + 2
+    beta, alpha = theta[: Ks + 1], theta[Ks + 1 : i]
+    xs = xo = None
+    if site_re:
+        xs = theta[i]; i += 1
+    if obs_re:
+        xo = theta[i]; i += 1
+    a = d = np.zeros(S)
+    o = np.zeros((S, P, J))
+    if site_re:
+        a = theta[i : i + S]; i += S
+        d = theta[i : i + S]; i += S
+    if obs_re:
+        o = theta[i : i + S * P * J].reshape(S, P, J); i += S * P * J
+    assert i == theta.size, "theta has wrong length"
+    return beta, alpha, xs, xo, a, d, o
+
+
+def occu_re_log_joint_enumerated(theta, site_covs, obs_covs, obs, *, site_random_effects=False,
+                                 obs_random_effects=False, dtype=np.float32, prior=True):
+    """occu.py:135-242 with the random-effect branches, op by op (no false positives, n_species = 1)."""
+    finfo = _finfo(dtype)
+    pr = prepare(site_covs, obs_covs, obs, dtype=dtype)
+    Sp, S, P, J = pr.y.shape
+    assert Sp == 1
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    beta, alpha, xs, xo, a, d, o = _split_re(theta, S, P, J, Ks, Ko, site_random_effects, obs_random_effects)
+    lp = 0.0
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+    if site_random_effects:
+        sd, l, _ = _half_normal_log(xs)
+        lp += l if prior else 0.0
+        lp += normal_log_prob(a, 0.0, sd).sum() + normal_log_prob(d, 0.0, sd).sum()  # sample sites, always scored
+    if obs_random_effects:
+        sdo, l, _ = _half_normal_log(xo)
+        lp += l if prior else 0.0
+        lp += normal_log_prob(o, 0.0, sdo).sum()
+    site_flat, site_shape = _flatten(pr.X.transpose(1, 0))
+    obs_flat, obs_shape = _flatten(pr.W.transpose(3, 2, 1, 0))
+    y = pr.y.transpose(3, 2, 1, 0)  # (J,P,S,1)
+    m = np.isfinite(y)
+    occ_linear = _linear(beta[None], site_flat).reshape(site_shape + (1,)) + a[:, None]  # (S,1)
+    psi = np.broadcast_to(expit(occ_linear), (P, S, 1))
+    z = np.array([0.0, 1.0]).reshape(2, 1, 1, 1, 1)
+    log_pz = bernoulli_log_prob(psi, z, finfo)
+    det_linear = (_linear(alpha[None], obs_flat).reshape(obs_shape + (1,)) + d[None, None, :, None]
+                  + o.transpose(2, 1, 0)[..., None])  # (J,P,S,1)
+    p = expit(det_linear)
+    v = np.where(m, y, 0.0)
+    ll = np.where(m, bernoulli_log_prob(z * p, v, finfo), 0.0)
+    site_ll = ll.sum(axis=1, keepdims=True) + log_pz
+    return float(lp + logsumexp(site_ll, axis=0).sum())
+
+
+def occu_re_logp_grad(theta, pr: Prepared, *, site_random_effects=False, obs_random_effects=False,
+                      dtype=np.float32, prior=True):
+    """Closed form + gradient of occu with random effects: the per-unit terms of occu_logp_grad with
+    eta_s + a_s and nu_spj + d_s + o_spj; the gradients w.r.t. a, d, o are ELEMENTWISE outputs."""
+    finfo = _finfo(dtype)
+    Sp, S, P, J = pr.y.shape
+    assert Sp == 1
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    beta, alpha, xs, xo, a, d, o = _split_re(theta, S, P, J, Ks, Ko, site_random_effects, obs_random_effects)
+    m = pr.mask[0]                                 # (S,P,J)
+    y = np.where(m, pr.y[0], 0.0)
+    eta = beta[0] + pr.X @ beta[1:] + a            # (S,)
+    nu = alpha[0] + pr.W @ alpha[1:] + d[:, None, None] + o  # (S,P,J)
+    psi, logpsi, log1mpsi, in_psi = _clamped_log_sigmoid_pair(eta, finfo)
+    p, logp_, log1mp, in_p = _clamped_log_sigmoid_pair(nu, finfo)
+    t1 = np.where(m, y * logp_ + (1 - y) * log1mp, 0.0)
+    dt1 = np.where(m & in_p, y - p, 0.0)
+    n1 = (m * y).sum(axis=2)
+    n0 = (m * (1 - y)).sum(axis=2)
+    L0 = n1 * np.log(finfo.tiny) + n0 * np.log1p(-finfo.tiny)
+    av = logpsi[:, None] + t1.sum(axis=2)          # (S,P)
+    bv = log1mpsi[:, None] + L0
+    ell = np.logaddexp(av, bv)
+    r = expit(av - bv)
+    d_eta = np.where(in_psi[:, None], r - psi[:, None], 0.0)   # (S,P)
+    d_nu = r[:, :, None] * dt1                                  # (S,P,J)
+    g_beta = np.concatenate([[d_eta.sum()], pr.X.T @ d_eta.sum(axis=1)])
+    g_alpha = np.concatenate([[d_nu.sum()], np.einsum("spj,spjk->k", d_nu, pr.W)])
+    lp = ell.sum()
+    if prior:
+        lp += normal_log_prob(beta).sum() + normal_log_prob(alpha).sum()
+        g_beta = g_beta - beta
+        g_alpha = g_alpha - alpha
+    grads = [g_beta, g_alpha]
+    tail = []
+    if site_random_effects:
+        sd, l, dl = _half_normal_log(xs)
+        lp += (l if prior else 0.0) + normal_log_prob(a, 0.0, sd).sum() + normal_log_prob(d, 0.0, sd).sum()
+        # d/dx of sum_s [ -a^2/(2 sd^2) - log sd ] (x = log sd) = sum a^2/sd^2 - S, twice (a and d)
+        grads.append([(a @ a + d @ d) / sd**2 - 2 * S + (dl if prior else 0.0)])
+        tail += [d_eta.sum(axis=1) - a / sd**2, d_nu.sum(axis=(1, 2)) - d / sd**2]
+    if obs_random_effects:
+        sdo, l, dl = _half_normal_log(xo)
+        lp += (l if prior else 0.0) + normal_log_prob(o, 0.0, sdo).sum()
+        grads.append([(o * o).sum() / sdo**2 - o.size + (dl if prior else 0.0)])
+        tail += [(d_nu - o / sdo**2).ravel()]
+    grad = np.concatenate([np.atleast_1d(g) for g in grads + tail]).astype(np.float64)
+    return float(lp), grad
+
 # ------------------------------------------------------------------ conveniences
 def logp_grad(model: str, theta, pr: Prepared, **kw):
     """Dispatch on model name; theta (D,) or (C, D) -> (logp[C], grad[C,D])."""

@@ -90,3 +90,29 @@ def test_site_invariances(model, seed, S, J, ks, ko):
         q = orc.logp_grad(model, th, orc.prepare(X, Wp, yp, Tp, dtype=np.float64), dtype=np.float64, prior=False, **kw)
         np.testing.assert_allclose(q[0], full[0], rtol=1e-11, atol=1e-11)
         np.testing.assert_allclose(q[1], full[1], rtol=1e-9, atol=1e-9)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 10_000), S=st.integers(1, 6), P=st.integers(1, 2), J=st.integers(1, 4),
+       ks=st.integers(0, 2), ko=st.integers(0, 2), site_re=st.booleans(), obs_re=st.booleans(), prior=st.booleans())
+def test_random_effects_groundwork(seed, S, P, J, ks, ko, site_re, obs_re, prior):
+    """Checker for the next row (site / observation random effects of occu, occu.py:168-228): closed form =
+    op-by-op enumerated form, elementwise gradients = finite differences, and it reduces to plain occu."""
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(S, ks))
+    W = rng.normal(size=(S, P, J, ko))
+    y = (rng.uniform(size=(1, S, P, J)) < 0.4).astype(float)
+    y[rng.uniform(size=y.shape) < 0.2] = np.nan
+    kw = dict(site_random_effects=site_re, obs_random_effects=obs_re, dtype=np.float64, prior=prior)
+    D = orc.occu_re_dims(S, P, J, ks, ko, site_re, obs_re)
+    th = 0.5 * rng.normal(size=D)
+    pr = orc.prepare(X, W, y, dtype=np.float64)
+    lp, g = orc.occu_re_logp_grad(th, pr, **kw)
+    f = lambda t: orc.occu_re_log_joint_enumerated(t, X, W, y, **kw)  # noqa: E731
+    assert abs(lp - f(th)) <= 1e-10 * max(1.0, abs(lp))
+    fd = orc.finite_difference_grad(f, th, h=1e-6)
+    assert np.abs(g - fd).max() <= 2e-6 * max(1.0, np.abs(g).max())
+    if not (site_re or obs_re):
+        ref_lp, ref_g = orc.occu_logp_grad(th, pr, dtype=np.float64, prior=prior)
+        assert abs(lp - ref_lp) <= 1e-12 * max(1.0, abs(ref_lp))
+        np.testing.assert_allclose(g, ref_g, rtol=1e-12, atol=1e-12)
