@@ -975,3 +975,36 @@ def site_summary(model: str, thetas, pr: Prepared, **kw):
     n = ells.shape[0]
     return dict(a1=np.mean(a1, axis=0), a2=np.mean(a2, axis=0), lppd=logsumexp(ells, axis=0) - np.log(n),
                 p_waic=ells.var(axis=0, ddof=1) if n > 1 else np.zeros(ells.shape[1]))
+
+
+# ------------------------------------------------------------------ per-observation outputs
+def occu_deterministic_sites(thetas, pr: Prepared, obs_raw=None):
+    """The deterministic sites the reference registers per draw (occu.py:207,221) in numpyro's own layout --
+    psi (draws, S, Sp=1), prob_detection (draws, J, P, S, 1) -- and the reference's per-observation closed form
+    `log_likelihood_manual` (evaluation/log_likelihood.py:55-98: psi*p form, clip(., 1e-10, 1 - 1e-10)),
+    (draws, Sp, S, P, J), NaN where the observation is NaN."""
+    thetas = np.atleast_2d(np.asarray(thetas, np.float64))
+    Ks, Ko = pr.X.shape[1], pr.W.shape[3]
+    eps = 1e-10
+    psis, pdets, lls = [], [], []
+    # the reference hands the RAW obs to log_likelihood_manual (only observation NaNs, not covariate NaNs)
+    yT = np.asarray(obs_raw, np.float64).transpose(3, 2, 1, 0) if obs_raw is not None else None
+    for th in thetas:
+        beta, alpha = th[: Ks + 1], th[Ks + 1 : Ks + Ko + 2]
+        psi = expit(beta[0] + pr.X @ beta[1:])[:, None]                        # (S, 1)
+        pdet = expit(alpha[0] + pr.W @ alpha[1:]).transpose(2, 1, 0)[..., None]  # (J, P, S, 1)
+        psis.append(psi)
+        pdets.append(pdet)
+        if yT is not None:
+            q = pdet * psi[None, None]
+            ll = np.log(np.clip(q, eps, 1 - eps)) * yT + np.log(np.clip(1 - q, eps, 1 - eps)) * (1 - yT)
+            lls.append(ll.transpose(3, 2, 1, 0))
+    return np.stack(psis), np.stack(pdets), (np.stack(lls) if lls else None)
+
+
+def lppd_manual(log_lik_manual, data: dict) -> float:
+    """evaluation/lppd.py:64-106: sum over valid observations of log-mean-exp over draws."""
+    valid = (np.isfinite(data["obs"]) & np.isfinite(data["obs_covs"]).all(axis=-1)[None, ...]
+             & np.isfinite(data["site_covs"]).all(axis=-1)[None, :, None, None])
+    ll = np.asarray(log_lik_manual)[:, valid]
+    return float(np.sum(logsumexp(ll, axis=0) - np.log(ll.shape[0])))
