@@ -56,6 +56,28 @@ METRIC = "logp+grad evals/sec (occu, 1M sites x 8 visits, chain-batched); NUTS E
 UNIT = "chain-evals/s"
 
 
+def host_threads():
+    """Threads the CPU arm may use: the process's CPU affinity, NOT OMP_NUM_THREADS (torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which made the round-1 reference arm single-threaded at N >= 2)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+L2_NOTE = "flushed between timed steps (256 MB memset outside the per-step CUDA events)"
+
+
+def build_config(args, model, X, W, chains, world, shard):
+    """The workload description both arms print (same keys, same values: the unit is per chain-eval)."""
+    return {"workload": args.workload, "likelihood": model, "strict_math": bool(args.strict_math),
+            "sites": int(X.shape[0] * (world if shard == "sites" else 1)), "visits": int(W.shape[2]),
+            "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]), "chains_per_gpu": chains,
+            "chains_total": chains * (world if shard == "chains" else 1), "sharding": shard,
+            "theta": "U(-2,2) per chain (init_to_uniform)" if args.theta == "uniform"
+            else "within 0.01 of the simulating truth (near the posterior mode)", "l2": L2_NOTE}
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -139,7 +161,7 @@ def make_data(workload, seed):
     return model, X, W, y, chains, shard
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, world):
     """CPU arm: the C/OpenMP restatement of the reference's path (the reference itself needs
     jax+numpyro, which are neither installed nor installable on this image), all host threads."""
     if rank != 0:
@@ -147,26 +169,29 @@ def run_reference(args, rank):
     from oracle import c_oracle
 
     model, X, W, y, chains, shard = make_data(args.workload, 0)
-    threads = c_oracle.max_threads()
+    if args.chains:
+        chains = args.chains
+    threads = host_threads()
     D = X.shape[1] + W.shape[3] + 2
     sample = args.cpu_chains
     th = np.random.default_rng(1).uniform(-2, 2, size=(sample, D))
     for _ in range(args.warmup):
-        c_oracle.occu_logp_grad(th[:1], X, W, y)
+        c_oracle.occu_logp_grad(th[:1], X, W, y, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        c_oracle.occu_logp_grad(th, X, W, y)
+        c_oracle.occu_logp_grad(th, X, W, y, nthreads=threads)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "sites": int(X.shape[0]), "visits": int(W.shape[2]),
-                   "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]),
-                   "note": "each step = %d chain-evals over the full dataset (bounded sample of the 1024-chain step)" % sample},
+        "config": build_config(args, model, X, W, chains, world, shard),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} chain-evals x {args.steps} steps, full 1M x 8 dataset, fp32, OpenMP {threads} threads"},
+                         "sample": f"each timed step = {sample} chain-evals over the full {X.shape[0]} x {W.shape[2]} "
+                                   f"dataset (a bounded sample of the {chains}-chain step; the unit is per chain-eval), "
+                                   f"{args.steps} steps, fp32, C/OpenMP restatement oracle/occu_oracle.c, {threads} threads "
+                                   f"(CPU affinity; OMP_NUM_THREADS ignored)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -187,6 +212,8 @@ def main():
     ap.add_argument("--nuts-warmup", type=int, default=200)
     ap.add_argument("--nuts-samples", type=int, default=100)
     ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s section")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the configs[2]/[3] lines (N=1)")
+    ap.add_argument("--no-site-sharded", action="store_true", help="skip the configs[4] block (N>1)")
     ap.add_argument("--strict-math", action="store_true", help="BL_FLAG_STRICT_MATH (libm expf/log1pf)")
     ap.add_argument("--theta", default="uniform", choices=["uniform", "mode"],
                     help="chain positions: U(-2,2) (init_to_uniform, default) or within 0.01 of the simulating truth "
@@ -198,7 +225,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, world)
 
     dist = None
     if world > 1:
@@ -320,50 +347,37 @@ def main():
     nuts = None
     if not args.no_nuts:
         nuts = run_nuts(args, lk, chains, rank, world, shard, dist)
+    site_sharded = None
+    if world > 1 and shard == "chains" and args.workload == "occu_1m_x8_c1024" and not args.no_site_sharded:
+        # the one multi-GPU mode with a data-path collective (BASELINE configs[4]); measured in the same run so
+        # that the driver's SCALE record carries it
+        site_sharded = run_site_sharded(args, dist, rank, world, local_rank)
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        alg_bytes = lk.algorithmic_bytes * chains  # C x B_eval per launch (per GPU)
         ms_launch = total_ms / args.steps
-        achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "likelihood": model, "strict_math": bool(args.strict_math), "sites": int(units_sites),
-                       "visits": int(W.shape[2]), "site_covs": int(X.shape[1]), "obs_covs": int(W.shape[3]),
-                       "chains_per_gpu": chains, "chains_total": chains_total, "sharding": shard,
-                       "theta": "U(-2,2) per chain (init_to_uniform)" if args.theta == "uniform"
-                       else "within 0.01 of the simulating truth (near the posterior mode)",
-                       "l2": "flushed between timed steps (256 MB memset outside the per-step CUDA events); "
-                             "packed dataset %.0f MB" % (lk.packed_bytes / 1e6)},
+            "config": build_config(args, model, X, W, chains, world, shard),
+            "packed_dataset_mb": lk.packed_bytes / 1e6,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(theta.nbytes),
                     "d2h_bytes_per_step": int(theta.nbytes + chains * es),
                     "note": "bl_eval_host: pinned H2D theta + kernel + D2H logp,grad per step; dataset packed once per fit"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": PROFILED_TRAFFIC.get(args.workload),
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "note": "algorithmic bytes = C x B_eval (SURVEY 8d): every chain's density is a full pass "
-                                 "over the data; tile reuse across the chain batch makes the kernel FP32/SFU-issue "
-                                 "bound, so frac > 1 is expected (see DESIGN.md, profiles/)"},
+            **rooflines(lib, local_rank, args.workload, model, lk, X, W, chains, ms_launch, args),
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
         }
-        if model == "occu" and lk.kernel_variant == 1 and chains >= 64 and args.dtype == "float32" and not args.strict_math:
-            # the unit that actually binds the chain kernel (profiles/): 3 MUFU (ex2, lg2, rcp) per logistic
-            # term, (J + 2) terms per (site, chain); B200 SFU = 16 lanes / SM / clock
-            mufu = 3.0 * (W.shape[2] + 2) * X.shape[0] * chains
-            sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
-            peak_mufu = 148 * 16 * sm_clock
-            line["roofline_sfu"] = {"bound": "sfu", "achieved": mufu / (ms_launch * 1e-3) / 1e12,
-                                    "peak": peak_mufu / 1e12, "unit": "T MUFU/s", "frac": mufu / (ms_launch * 1e-3) / peak_mufu,
-                                    "note": "secondary roofline: the kernel is issue/SFU bound, not HBM bound"}
         if exchange_check is not None:
             line["exchange_check"] = exchange_check
         if nuts is not None:
             line["nuts"] = nuts
+        if site_sharded is not None:
+            line["site_sharded"] = site_sharded
+        if world == 1 and args.workload == "occu_1m_x8_c1024" and not args.no_other_workloads:
+            line["other_workloads"] = other_workloads(lib, local_rank, args)
         if world == 1 and model == "occu" and args.dtype == "float32" and not args.strict_math:
             # the same evaluation with libm expf / log1pf / IEEE division (BL_FLAG_STRICT_MATH), for the record:
             # the default kernels use bounded-error SFU forms (DESIGN.md "Numerics"); never fatal for the line
@@ -383,6 +397,199 @@ def main():
     lk.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+# Per-(unit, chain) instruction counts of the shipped lane = chain kernels, from the committed ncu captures
+# (profiles/; sm__inst_executed.sum and the MUFU share of it divided by units x chains of the profiled launch).
+# They turn a measured time into an achieved issue / SFU rate; the peaks are measured by bl_pipe_peak.
+PROFILED = {
+    # workload: (warp-instructions per (unit, chain) x 32 lanes -> per lane, MUFU per (unit, chain), DRAM bytes / launch, source)
+    "occu_1m_x8_c1024": dict(instr=270.0, mufu=30.0, traffic=236_505_600, src="profiles/r01_occu_chain_v6.txt"),
+    "occu_cop_500k_x12": dict(instr=368.0, mufu=44.0, traffic=None, src="profiles/r01_occu_cop_chain_v1.txt"),
+    "occu_rn_200k_x10_k50": dict(instr=14886.0, mufu=None, traffic=None, src="profiles/r01_occu_rn_chain_v2.txt"),
+}
+_PIPE_PEAKS = {}
+
+
+def pipe_peaks(lib, device):
+    """Measured MUFU lane-ops/s and warp-instruction issue/s of this GPU (csrc/microbench.cu), once per process."""
+    if device not in _PIPE_PEAKS:
+        from biolith_b200 import _lib
+
+        out = {}
+        for which, key in ((0, "mufu_per_s"), (1, "issue_per_s")):
+            v, clk = C.c_double(), C.c_double()
+            _lib.check(lib.bl_pipe_peak(device, which, C.byref(v), C.byref(clk)), "bl_pipe_peak")
+            out[key] = float(v.value)
+        _PIPE_PEAKS[device] = out
+    return _PIPE_PEAKS[device]
+
+
+def rooflines(lib, device, workload, model, lk, X, W, chains, ms_launch, args):
+    """`roofline` = the unit that BINDS the dominant kernel.  For the chain-batched kernels that is instruction
+    issue (and the SFU pipe next to it): a staged site tile is reused by every chain of the block, so physical
+    DRAM traffic is ~1.6x the packed dataset per launch (0.4 % of HBM).  The SURVEY 8d figure -- C x B_eval
+    algorithmic bytes per launch over the HBM peak -- is kept as `roofline_hbm_algorithmic`."""
+    peak_hbm, peak_src = measured_peak_hbm()
+    alg_bytes = lk.algorithmic_bytes * chains
+    t = ms_launch * 1e-3
+    units = float(lk.shape["n_sites"] * lk.shape["n_periods"])
+    out = {}
+    hbm = {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
+           "frac": alg_bytes / t / 1e9 / peak_hbm, "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": int(alg_bytes),
+           "note": "SURVEY 8d definition: C x B_eval algorithmic bytes per launch (every chain's density is a full "
+                   "pass over the data); with tile reuse across the chain batch frac > 1 is expected and is NOT a "
+                   "physical bandwidth"}
+    prof = PROFILED.get(workload)
+    chain_kernel = (prof is not None and args.dtype == "float32" and not args.strict_math and chains >= 32
+                    and lk.kernel_variant == 1)
+    if chain_kernel:
+        pk = pipe_peaks(lib, device)
+        winstr = prof["instr"] * units * chains  # warp-instructions x lanes... = thread-instructions
+        issue_rate = winstr / 32.0 / t           # warp-instructions per second
+        out["roofline"] = {
+            "bound": "issue", "achieved": issue_rate / 1e9, "peak": pk["issue_per_s"] / 1e9, "unit": "G warp-instr/s",
+            "frac": issue_rate / pk["issue_per_s"], "traffic": prof["traffic"],
+            "instr_per_unit_chain": prof["instr"], "instr_source": prof["src"],
+            "peak_source": "measured: bl_pipe_peak(issue), independent FFMA chains on all 4 schedulers of every SM",
+            "note": "binding unit of the lane = chain kernel; `traffic` = DRAM bytes per launch from the ncu capture"}
+        if prof["mufu"]:
+            mufu_rate = prof["mufu"] * units * chains / t
+            out["roofline_sfu"] = {"bound": "sfu", "achieved": mufu_rate / 1e12, "peak": pk["mufu_per_s"] / 1e12,
+                                   "unit": "T MUFU/s", "frac": mufu_rate / pk["mufu_per_s"],
+                                   "mufu_per_unit_chain": prof["mufu"],
+                                   "peak_source": "measured: bl_pipe_peak(mufu), MUFU.EX2 chains"}
+        out["roofline_hbm_algorithmic"] = hbm
+    else:
+        hbm["traffic"] = prof["traffic"] if prof else None
+        out["roofline"] = hbm
+    return out
+
+
+def _time_eval(lib, lk, theta, device, steps, warmup=3):
+    """ms per evaluation (CUDA events on the launch stream, L2 flushed between steps) for a resident theta."""
+    import biolith_b200 as bb
+    from biolith_b200 import _lib
+
+    stream = C.c_void_p()
+    _lib.check(lib.bl_stream_create(device, C.byref(stream)), "bl_stream_create")
+    n = theta.shape[0]
+    es = theta.dtype.itemsize
+    d_th, d_lp, d_gr = (bb.DeviceBuffer(theta.nbytes, device), bb.DeviceBuffer(n * es, device),
+                        bb.DeviceBuffer(theta.nbytes, device))
+    d_th.upload(theta, stream)
+    ms = []
+    for i in range(warmup + steps):
+        _lib.check(lib.bl_flush_l2(device, stream), "flush")
+        v = lk.eval_timed(d_th.ptr, n, d_lp.ptr, d_gr.ptr, stream, iters=1)
+        if i >= warmup:
+            ms.append(v)
+    for b in (d_th, d_lp, d_gr):
+        b.free()
+    lib.bl_stream_destroy(stream)
+    return float(np.mean(ms))
+
+
+def other_workloads(lib, device, args):
+    """BASELINE configs[2] (occu_rn 200k x 10, K = 50) and configs[3] (occu_cop 500k x 12, NaN-masked) timed in the
+    same run so that the driver's record carries them; same timing rules, fewer steps."""
+    import biolith_b200 as bb
+
+    out = {}
+    for wl, chains in (("occu_rn_200k_x10_k50", 256), ("occu_cop_500k_x12", 1024)):
+        try:
+            model, X, W, y, _, _ = make_data(wl, 0)
+            T = make_data.session_duration
+            with bb.OccupancyLikelihood(model, X, W, y, T, device=device, max_chains=chains,
+                                        **MODEL_KW.get(model, {})) as lk:
+                theta = np.random.default_rng(1000).uniform(-2, 2, size=(chains, lk.theta_dim)).astype(np.float32)
+                ms = _time_eval(lib, lk, theta, device, steps=5)
+                sub = argparse.Namespace(**{**vars(args), "workload": wl})
+                entry = {"ms_per_step": ms, "value": chains / (ms * 1e-3), "unit": UNIT,
+                         "config": build_config(sub, model, X, W, chains, 1, "chains"),
+                         **rooflines(lib, device, wl, model, lk, X, W, chains, ms, args)}
+            out[wl] = entry
+        except Exception as exc:  # noqa: BLE001 - never fatal for the headline line
+            out[wl] = {"error": str(exc)[:300]}
+    return out
+
+
+def run_site_sharded(args, dist, rank, world, device):
+    """BASELINE configs[4]: occu, sites sharded over the ranks, 256 chains, one exchange of the [C, 1+D] fp64 sums
+    per evaluation.  Weak (2M sites per rank) and strong (a fixed 16M-site problem cut into `world` shards) sizes,
+    both exchange modes, the exchange cost isolated (attached minus plain evaluation of the same shard), and the
+    summed result checked against the fp64 C oracle evaluated on every rank's own shard."""
+    import torch
+
+    import biolith_b200 as bb
+    from biolith_b200 import sharded
+    from oracle import c_oracle
+
+    lib = bb._lib.load()
+    chains = 256
+    out = {"chains": chains, "world": world}
+    sizes = {"weak_2m_sites_per_rank": 2_000_000}
+    if 16_000_000 // world != 2_000_000:
+        sizes[f"strong_16m_sites_over_{world}_ranks"] = 16_000_000 // world
+    theta = np.random.default_rng(77).uniform(-2, 2, size=(chains, 10)).astype(np.float32)  # same on all ranks
+
+    def tmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    for label, n_sites in sizes.items():
+        model, kw, _, _ = WORKLOADS["occu_sites16m_c256"]
+        WORKLOADS["_site_tmp"] = (model, {**kw, "n_sites": n_sites}, chains, "sites")
+        _, X, W, y, _, _ = make_data("_site_tmp", rank)
+        entry = {"sites_per_rank": n_sites, "sites_total": n_sites * world}
+        with bb.OccupancyLikelihood(model, X, W, y, None, device=device, max_chains=chains) as plain:
+            dist.barrier()
+            entry["ms_per_eval_local_only"] = tmax(_time_eval(lib, plain, theta, device, steps=args.steps))
+        ref = None
+        for mode in ("p2p", "nccl"):
+            with bb.OccupancyLikelihood(model, X, W, y, None, device=device, max_chains=chains) as lk:
+                sharded.attach_site_sharding(lk, dist, rank, world, chains, mode=mode)
+                dist.barrier()
+                ms = tmax(_time_eval(lib, lk, theta, device, steps=args.steps))
+                lp, gr = lk.logp_and_grad(theta)
+                if sharded.comm_error(lk):
+                    raise RuntimeError("cross-GPU exchange timed out")
+                got = np.concatenate([lp.astype(np.float64)[:, None], gr.astype(np.float64)], axis=1)
+                g = torch.tensor(got, dtype=torch.float64, device="cuda")
+                gmax, gmin = g.clone(), g.clone()
+                dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+                if ref is None:
+                    # fp64 C oracle on THIS rank's shard (4 chains, likelihood only), summed over ranks, priors once
+                    k = 4
+                    th64 = theta[:k].astype(np.float64)
+                    threads = max(1, host_threads() // world)
+                    olp, ogr = c_oracle.occu_logp_grad(th64, X, W, y, dtype=np.float64, prior=False, nthreads=threads)
+                    t = torch.tensor(np.concatenate([olp[:, None], ogr], axis=1), dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t)
+                    ref = t.cpu().numpy()
+                    ref[:, 0] += (-0.5 * th64 ** 2 - 0.9189385332046727).sum(axis=1)
+                    ref[:, 1:] -= th64
+                err = np.abs(got[:ref.shape[0]] - ref) / np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
+                err_lp = np.abs(got[:ref.shape[0], 0] - ref[:, 0]) / np.abs(ref[:, 0])
+                entry[mode] = {
+                    "ms_per_eval": ms, "chain_evals_per_s": chains / (ms * 1e-3),
+                    "exchange_ms": ms - entry["ms_per_eval_local_only"],
+                    "max_rel_err_logp_vs_fp64_c_oracle": float(err_lp.max()),
+                    "max_rel_err_grad_vs_fp64_c_oracle": float(err[:, 1:].max()),
+                    "bit_identical_across_ranks": bool(torch.equal(gmax, gmin)),
+                }
+                lib.bl_dataset_detach_comm(lk.handle)
+            dist.barrier()
+        out[label] = entry
+        del X, W, y
+    WORKLOADS.pop("_site_tmp", None)
+    out["note"] = ("exchange = [C, 1+D] fp64 sums (22 KB): 'p2p' is ONE fused kernel over CUDA-IPC peer memory "
+                   "(publish, flag, rank-ordered sum, priors), 'nccl' is ncclAllReduce + finalize; oracle check = fp64 "
+                   "C/OpenMP restatement on every rank's own shard, summed with an fp64 all-reduce")
+    return out if rank == 0 else None
 
 
 def run_nuts(args, lk, chains, rank, world, shard, dist):
@@ -449,30 +656,22 @@ def shard_is_chains(workload):
     return WORKLOADS[workload][3] == "chains"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the eval kernel (ncu --set full), by workload
-PROFILED_TRAFFIC = {
-    # profiles/r01_occu_chain_v6.txt (final round-1 binary): 227.34 MB read + 9.17 MB written per launch
-    # (packed dataset: 128 MB; the 4 chain chunks re-read tiles mostly from L2)
-    "occu_1m_x8_c1024": 236_505_600,
-}
-
-
 def cpu_baseline(X, W, y, D, sample, model="occu", T=None):
     from oracle import c_oracle
 
-    threads = c_oracle.max_threads()
+    threads = host_threads()
     th = np.random.default_rng(1).uniform(-2, 2, size=(sample, D))
     if model == "occu_cop":  # config 4: the C restatement computes in double (clamp constants of fp32)
         def run(t):
-            return c_oracle.occu_cop_logp_grad(t, X, W, y, T, fp_constant=True)
+            return c_oracle.occu_cop_logp_grad(t, X, W, y, T, fp_constant=True, nthreads=threads)
         arith = "fp64-arithmetic"
     elif model == "occu_rn":  # config 3
         def run(t):
-            return c_oracle.occu_rn_logp_grad(t, X, W, y, **MODEL_KW["occu_rn"])
+            return c_oracle.occu_rn_logp_grad(t, X, W, y, nthreads=threads, **MODEL_KW["occu_rn"])
         arith = "fp64-arithmetic"
     else:
         def run(t):
-            return c_oracle.occu_logp_grad(t, X, W, y)
+            return c_oracle.occu_logp_grad(t, X, W, y, nthreads=threads)
         arith = "fp32"
     run(th[:1])
     t0 = time.perf_counter()

@@ -30,8 +30,8 @@ BL_API void bl_xla_eval(void* stream, void** buffers, const char* opaque, size_t
     }
   }
   if (err && status) {
-    static xla_set_failure_fn set_failure =
-        (xla_set_failure_fn)dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure");
+    // error path only: look the callback up every time (the runtime that exports it may be loaded after us)
+    xla_set_failure_fn set_failure = (xla_set_failure_fn)dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure");
     if (set_failure) set_failure(status, err, strlen(err));
   }
 }

@@ -27,8 +27,10 @@ def _fft_next_fast_len(n: int) -> int:
         n += 1
 
 
-def autocorrelation(x, axis=0):
-    """Unbiased (divide by N - lag) autocorrelation along ``axis`` via FFT, normalised at lag 0."""
+def autocorrelation(x, axis=0, bias=True):
+    """Autocorrelation along ``axis`` via FFT, normalised at lag 0.  ``bias=True`` (numpyro >= 0.18's default,
+    the version the reference pins: pyproject.toml:26) keeps the 1/N estimator; ``bias=False`` divides lag k by
+    N - k (the older default)."""
     x = np.asarray(x, dtype=np.float64)
     N = x.shape[axis]
     M = _fft_next_fast_len(N)
@@ -38,15 +40,16 @@ def autocorrelation(x, axis=0):
     freq = np.fft.rfft(centered, n=M2, axis=-1)
     power = freq.real**2 + freq.imag**2
     ac = np.fft.irfft(power, n=M2, axis=-1)[..., :N]
-    ac = ac / np.arange(N, 0.0, -1)
+    if not bias:
+        ac = ac / np.arange(N, 0.0, -1)
     with np.errstate(invalid="ignore", divide="ignore"):
         ac = ac / ac[..., :1]
     return np.swapaxes(ac, axis, -1)
 
 
-def autocovariance(x, axis=0):
+def autocovariance(x, axis=0, bias=True):
     x = np.asarray(x, dtype=np.float64)
-    return autocorrelation(x, axis) * x.var(axis=axis, keepdims=True)
+    return autocorrelation(x, axis, bias) * x.var(axis=axis, keepdims=True)
 
 
 def _chain_variance_stats(x):
@@ -78,12 +81,12 @@ def split_gelman_rubin(x):
     return gelman_rubin(new)
 
 
-def effective_sample_size(x):
+def effective_sample_size(x, bias=True):
     """numpyro.diagnostics.effective_sample_size: x (num_chains, num_draws, ...) -> n_eff (...)."""
     x = np.asarray(x, dtype=np.float64)
     assert x.ndim >= 2 and x.shape[1] >= 2
     C, N = x.shape[0], x.shape[1]
-    gamma_k_c = autocovariance(x, axis=1)  # (C, N, ...)
+    gamma_k_c = autocovariance(x, axis=1, bias=bias)  # (C, N, ...)
     var_within, var_estimator = _chain_variance_stats(x)
     with np.errstate(invalid="ignore", divide="ignore"):
         rho_k = 1.0 - (var_within - gamma_k_c.mean(axis=0)) / var_estimator

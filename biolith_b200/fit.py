@@ -19,21 +19,13 @@ import numpy as np
 from . import diagnostics as _diag
 from ._lib import BiolithB200Error
 from .likelihood import OccupancyLikelihood, _as_numpy
-from .models import REJECTED_IF_SET, SUPPORTED
+from .data import prepare_data, rename_samples
+from .models import SUPPORTED, model_options
 from .nuts import NutsSampler
 
 FitResult = namedtuple("FitResult", ["samples", "mcmc"])
 
 _MAX_DETERMINISTIC_ELEMS = 50_000_000
-
-
-def _covariate_names(arr, n):
-    if hasattr(arr, "columns"):
-        cols = list(arr.columns)
-        if getattr(arr.columns, "nlevels", 1) > 1:
-            cols = list(arr.columns.get_level_values(-1).unique())
-        return ["intercept"] + [str(c) for c in cols][:n]
-    return [str(0)] + [str(i + 1) for i in range(n)]
 
 
 class MCMCResult:
@@ -99,40 +91,11 @@ def fit(
     if init_strategy is not None and init_strategy != "map":
         raise BiolithB200Error(-2, "fit", "init_strategy: only None (init_to_uniform(radius=2), the reference's default) "
                                "or \"map\" (start at the posterior mode, biolith_b200.optim) are supported")
-    for k, default in REJECTED_IF_SET.items():
-        v = kwargs.get(k, default)
-        if v is not None and v is not False and v is not default:
-            raise BiolithB200Error(-2, "fit", f"{k} is outside the accelerated path (no fallback)")
-    for k in ("regressor_occ", "regressor_det", "regressor_abu"):
-        r = kwargs.get(k)
-        if r is not None and getattr(r, "__name__", "") != "LinearRegression":
-            raise BiolithB200Error(-2, "fit", f"{k}={r!r}: only LinearRegression is accelerated")
-    prior_kw = {}
-    for k, tgt in (("prior_beta", "prior_beta"), ("prior_alpha", "prior_alpha")):
-        pr = kwargs.get(k)
-        if pr is not None:
-            loc, scale = getattr(pr, "loc", None), getattr(pr, "scale", None)
-            if loc is None or scale is None or type(pr).__name__ != "Normal":
-                raise BiolithB200Error(-2, "fit", f"{k}: only Normal(loc, scale) priors are accelerated")
-            prior_kw[tgt] = (float(loc), float(scale))
-    if name == "occu_cs":
-        # occu_cs.py:29-30: one distribution or a (f = 0, f = 1) pair; the kernels carry one Normal(0, s) / Gamma(a, b)
-        for k, kind, fields in (("prior_mu", "Normal", ("loc", "scale")), ("prior_sigma", "Gamma", ("concentration", "rate"))):
-            pr = kwargs.get(k)
-            if pr is None:
-                continue
-            if isinstance(pr, tuple) or type(pr).__name__ != kind or (kind == "Normal" and float(pr.loc) != 0.0):
-                raise BiolithB200Error(-2, "fit", f"{k}: only a single zero-centred {kind} prior is accelerated")
-            vals = tuple(float(getattr(pr, f)) for f in fields)
-            prior_kw["prior_mu_scale" if k == "prior_mu" else "prior_sigma"] = vals[1] if k == "prior_mu" else vals
-    n_species = kwargs.get("n_species", 1)
-    site_names = _covariate_names(site_covs, _as_numpy(site_covs).shape[1])
-    obs_np = _as_numpy(obs_covs)
-    obs_names = _covariate_names(obs_covs, obs_np.shape[-1] if obs_np.ndim >= 3 else 1)
-    if kwargs.pop("ell", None) is not None:
-        pass  # simulate() returns ell even without coords; meaningless without a spatial effect
-    fpc = bool(kwargs.get("false_positives_constant", False))
-    fpu = bool(kwargs.get("false_positives_unoccupied", False))
+    fpc, fpu, max_abundance, prior_kw = model_options(name, kwargs)
+    site_covs, obs_covs, obs, session_duration, site_names, obs_names = prepare_data(
+        site_covs, obs_covs, obs, session_duration)
+    if site_covs is None or obs_covs is None or obs is None:
+        raise BiolithB200Error(-1, "fit", "site_covs, obs_covs and obs are required (prior predictive is not accelerated)")
     from .likelihood import ensure_period_dim
 
     _, _, obs_np4, _ = ensure_period_dim(None, None, _as_numpy(obs), None)
@@ -144,7 +107,7 @@ def fit(
     parts = []
     for sp in range(n_sp):
         # species are independent problems sharing the covariates (one handle each, occu.py:182-186)
-        parts.append(_fit_one(name, site_covs, obs_covs, obs_np4[sp:sp + 1], session_duration, fpc, fpu, kwargs,
+        parts.append(_fit_one(name, site_covs, obs_covs, obs_np4[sp:sp + 1], session_duration, fpc, fpu, max_abundance,
                               dtype, device, num_chains, num_warmup, num_samples, random_seed + 7919 * sp,
                               max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods,
                               init_strategy))
@@ -166,13 +129,13 @@ def fit(
     return FitResult(samples, mcmc)
 
 
-def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs, dtype, device, num_chains,
+def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abundance, dtype, device, num_chains,
              num_warmup, num_samples, seed, max_tree_depth, target_accept_prob, timeout, prior_kw, n_periods,
              init_strategy=None):
     """One species: pack, sample on the device, return (grouped samples, extra fields, info)."""
     lk = OccupancyLikelihood(
         name, site_covs, obs_covs, obs, session_duration, false_positives_constant=fpc,
-        false_positives_unoccupied=fpu, max_abundance=kwargs.get("max_abundance", 100), dtype=dtype, prior=True,
+        false_positives_unoccupied=fpu, max_abundance=max_abundance, dtype=dtype, prior=True,
         device=device, max_chains=num_chains, **prior_kw)
     init_params = None
     if init_strategy == "map":
@@ -232,17 +195,3 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, kwargs,
     info["site_summary"] = lk.site_summary(thin)
     lk.close()
     return grouped, extra, info
-
-
-def rename_samples(samples, site_covs_names=None, obs_covs_names=None):
-    """Same renaming as biolith/utils/data.py:145-165."""
-    samples = dict(samples)
-    if site_covs_names is not None and "beta" in samples:
-        beta = samples.pop("beta")
-        for i, n in enumerate(site_covs_names):
-            samples[f"cov_state_{n}"] = beta[..., i]
-    if obs_covs_names is not None and "alpha" in samples:
-        alpha = samples.pop("alpha")
-        for i, n in enumerate(obs_covs_names):
-            samples[f"cov_det_{n}"] = alpha[..., i]
-    return samples

@@ -1,11 +1,13 @@
 """jax.ffi binding of the accelerated path + drop-in NumPyro models.
 
-UNTESTED IN THIS REPO'S CI: jax / numpyro / funsor are not installed (and not installable) in the
-build image or on the GPU boxes, so this module is exercised only by its import guard
-(tests/test_abi.py).  Everything below goes through the same C ABI (`bl_dataset_create`, `bl_eval`
-via `bl_xla_eval`) that the ctypes tests cover on the GPU; the jax-facing part follows the
-documented JAX >= 0.5 FFI API (`jax.ffi.register_ffi_target`, `jax.ffi.pycapsule`,
-`jax.ffi.ffi_call`) and must be verified on a box that has jax ("verification").
+jax / numpyro / funsor are not installed (and not installable) in the build image or on the GPU boxes.
+What IS exercised on the GPU (tests/test_gpu_xla_boundary.py): `bl_xla_eval` called exactly as XLA's legacy
+custom-call ABI calls it (non-default stream, `void* buffers[3]`, opaque bytes, status + failure callback), and
+this module's registration / custom_vjp / custom_vmap folding / drop-in models run against a minimal stand-in
+for the handful of jax + numpyro entry points they use (tests/fakejax.py + oracle/refshim.py), with the result
+compared to the executed reference bodies.  What remains unverified is only that the installed JAX accepts these
+calls as documented for JAX >= 0.5 (`jax.ffi.register_ffi_target`, `jax.ffi.pycapsule`, `jax.ffi.ffi_call`);
+see INTEGRATION.md, "verification".
 
 Usage with the unmodified reference:
 
@@ -23,6 +25,8 @@ enumeration + masked likelihood (occu.py:182-242) are replaced by
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
+
 try:  # pragma: no cover - jax is absent in this image
     import jax
     import jax.numpy as jnp
@@ -94,49 +98,80 @@ def make_loglik(likelihood: OccupancyLikelihood):
         return (ct[..., None] * g,)
 
     loglik.defvjp(fwd, bwd)
+    loglik.batched_call = _call  # the custom_vmap'd primitive (tests fold a chain axis through it)
     return loglik
 
 
 def _drop_in(model_name):
-    def model(site_covs, obs_covs, coords=None, ell=1.0, session_duration=None,
-              false_positives_constant=False, false_positives_unoccupied=False, max_abundance=100, obs=None,
-              n_species=1, prior_beta=None, prior_alpha=None, prior_mu=None, prior_sigma=None, **unsupported):
+    def model(site_covs, obs_covs, coords=None, ell=1.0, session_duration=None, obs=None, **kwargs):
         _require_jax()
         import numpyro
         import numpyro.distributions as dist
         from biolith.regression import LinearRegression  # the reference's own regressor, unchanged
 
-        if coords is not None or any(unsupported.get(k) for k in ("site_random_effects", "obs_random_effects")):
-            raise _lib.BiolithB200Error(-2, model_name, "spatial / random effects are outside the accelerated path")
+        from .models import model_options
+
         if obs is None:
             raise _lib.BiolithB200Error(-2, model_name, "prior predictive (obs=None) is outside the accelerated path")
-        lk = _handle_cache(model_name, site_covs, obs_covs, obs, session_duration, false_positives_constant,
-                           false_positives_unoccupied, max_abundance)
+        # same whitelist as biolith_b200.fit: unknown keys / options outside the path raise.  Priors are NOT
+        # restricted here: every prior stays a numpyro sample site below, the kernel is likelihood-only
+        from .models import KEYWORDS
+
+        unknown = set(kwargs) - KEYWORDS[model_name]
+        if unknown:
+            raise _lib.BiolithB200Error(-1, model_name, f"unknown keyword(s): {sorted(unknown)}")
+        fpc, fpu, max_abundance, _ = model_options(
+            model_name, dict({k: v for k, v in kwargs.items() if not k.startswith("prior_")}, coords=coords))
+        if obs.shape[0] != 1:
+            raise _lib.BiolithB200Error(-2, model_name, "n_species > 1: one drop-in model per species")
+        lk = dataset_handle(model_name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abundance)
         loglik = make_loglik(lk)
         extras = []
-        if model_name == "occu_cs":
-            # occu_cs.py:146-154, unchanged sample sites; the kernel takes the extras in numpyro's own
-            # unconstrained coordinates, so jax differentiates through these three elementary maps
-            pm = prior_mu if isinstance(prior_mu, tuple) else (prior_mu or dist.Normal(0, 10),) * 2
-            ps = prior_sigma if isinstance(prior_sigma, tuple) else (prior_sigma or dist.Gamma(5, 1),) * 2
+        # the extras keep the reference's sample sites AND its priors (whatever distribution the caller passes:
+        # the prior stays with numpyro); the kernel takes them in numpyro's own unconstrained coordinates, so jax
+        # differentiates through these elementary maps
+        if model_name == "occu_cs":  # occu_cs.py:146-154
+            pm, ps = kwargs.get("prior_mu", dist.Normal(0, 10)), kwargs.get("prior_sigma", dist.Gamma(5, 1))
+            pm = pm if isinstance(pm, tuple) else (pm, pm)
+            ps = ps if isinstance(ps, tuple) else (ps, ps)
             mu0 = numpyro.sample("mu0", pm[0])
             mu1 = numpyro.sample("mu1", dist.TruncatedDistribution(pm[1], low=mu0))
             sigma0 = numpyro.sample("sigma0", ps[0])
             sigma1 = numpyro.sample("sigma1", ps[1])
             extras += [mu0, jnp.log(mu1 - mu0), jnp.log(sigma0), jnp.log(sigma1)]
-        elif model_name == "occu_cop":
-            if false_positives_constant:
-                extras.append(jnp.log(numpyro.sample("rate_fp_constant", dist.Exponential())))
-            if false_positives_unoccupied:
-                extras.append(jnp.log(numpyro.sample("rate_fp_unoccupied", dist.Exponential())))
-        else:
-            if false_positives_constant:
-                extras.append(jax.scipy.special.logit(numpyro.sample("prob_fp_constant", dist.Beta(2, 5))))
-            if false_positives_unoccupied:
-                extras.append(jax.scipy.special.logit(numpyro.sample("prob_fp_unoccupied", dist.Beta(2, 5))))
+        elif model_name == "occu_cop":  # occu_cop.py:160-171
+            if fpc:
+                extras.append(jnp.log(numpyro.sample(
+                    "rate_fp_constant", kwargs.get("prior_rate_fp_constant", dist.Exponential()))))
+            if fpu:
+                extras.append(jnp.log(numpyro.sample(
+                    "rate_fp_unoccupied", kwargs.get("prior_rate_fp_unoccupied", dist.Exponential()))))
+        else:  # occu.py:146-157, occu_rn.py:133-137
+            if fpc:
+                extras.append(jax.scipy.special.logit(numpyro.sample(
+                    "prob_fp_constant", kwargs.get("prior_prob_fp_constant", dist.Beta(2, 5)))))
+            if fpu:
+                extras.append(jax.scipy.special.logit(numpyro.sample(
+                    "prob_fp_unoccupied", kwargs.get("prior_prob_fp_unoccupied", dist.Beta(2, 5)))))
+        X = jnp.nan_to_num(jnp.asarray(site_covs))  # occu.py:141-142
+        W = jnp.nan_to_num(jnp.asarray(obs_covs))
         with numpyro.plate("species", 1, dim=-1):
-            reg_occ = LinearRegression("beta", site_covs.shape[1], prior=prior_beta or dist.Normal())
-            reg_det = LinearRegression("alpha", obs_covs.shape[-1], prior=prior_alpha or dist.Normal())
+            reg_occ = LinearRegression("beta", site_covs.shape[1], prior=kwargs.get("prior_beta", dist.Normal()))
+            reg_det = LinearRegression("alpha", obs_covs.shape[-1], prior=kwargs.get("prior_alpha", dist.Normal()))
+            # deterministic sites of the reference with its shapes (occu.py:207,221; occu_rn.py:188,205;
+            # occu_cop.py:222,236): (S, Sp) and (J, P, S, Sp).  Plain jnp -- evaluated once per kept draw by
+            # numpyro's postprocess_fn, never per leapfrog (XLA dead-code-eliminates them from potential_fn)
+            occ_linear = reg_occ(X)                                                     # (S, Sp)
+            det_linear = reg_det(W.transpose((3, 2, 1, 0)).reshape(W.shape[3], -1).T)   # (J*P*S, Sp)
+            det_linear = det_linear.reshape(W.shape[2], W.shape[1], W.shape[0], -1)
+            if model_name in ("occu_rn", "nmixture"):
+                numpyro.deterministic("abundance", jnp.exp(occ_linear))
+            else:
+                numpyro.deterministic("psi", jax.nn.sigmoid(occ_linear))
+            if model_name == "occu_cop":
+                numpyro.deterministic("rate_detection", jnp.exp(det_linear))
+            elif model_name != "occu_cs":
+                numpyro.deterministic("prob_detection", jax.nn.sigmoid(det_linear))
         theta = jnp.concatenate([reg_occ.coef[0], reg_det.coef[0]] + [jnp.atleast_1d(e) for e in extras])
         numpyro.factor("loglik", loglik(theta))
 
@@ -144,22 +179,57 @@ def _drop_in(model_name):
     return model
 
 
-_handles = {}
+# ---- packed datasets: one per distinct (model, options, DATA CONTENT) --------------------------------------
+# The reference's fit() builds fresh arrays on every call, so object identity says nothing: the key is a digest of
+# the bytes.  A small LRU bounds the HBM held by finished fits; close_datasets() frees everything explicitly.
+_handles = OrderedDict()
+MAX_CACHED_DATASETS = 4
 
 
-def _handle_cache(model_name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abundance):
-    """One packed dataset per (model, data identity): packing happens once per fit, like the
-    reference's trace-time constant folding of the NaN mask (occu.py:136-142)."""
+def _digest(*arrays) -> str:
+    import hashlib
+
     import numpy as np
 
-    key = (model_name, id(site_covs), id(obs_covs), id(obs), fpc, fpu, max_abundance)
-    if key not in _handles:
-        _handles[key] = OccupancyLikelihood(
-            model_name, np.asarray(site_covs), np.asarray(obs_covs), np.asarray(obs),
-            None if session_duration is None else np.asarray(session_duration),
-            false_positives_constant=fpc, false_positives_unoccupied=fpu, max_abundance=max_abundance,
-            prior=False)  # priors stay with numpyro's sample sites
-    return _handles[key]
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        if a is None:
+            h.update(b"<none>")
+            continue
+        a = np.ascontiguousarray(np.asarray(a))
+        h.update(str((a.shape, a.dtype.str)).encode())
+        h.update(a.view(np.uint8).reshape(-1).data)
+    return h.hexdigest()
+
+
+def dataset_handle(model_name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abundance):
+    """Packing happens once per distinct dataset, like the reference's trace-time constant folding of the NaN
+    mask (occu.py:136-142); the model function itself is re-traced by numpyro several times per fit."""
+    import numpy as np
+
+    key = (model_name, bool(fpc), bool(fpu), int(max_abundance),
+           _digest(site_covs, obs_covs, obs, session_duration if model_name == "occu_cop" else None))
+    lk = _handles.get(key)
+    if lk is not None:
+        _handles.move_to_end(key)
+        return lk
+    lk = OccupancyLikelihood(
+        model_name, np.asarray(site_covs), np.asarray(obs_covs), np.asarray(obs),
+        None if session_duration is None else np.asarray(session_duration),
+        false_positives_constant=fpc, false_positives_unoccupied=fpu, max_abundance=max_abundance,
+        prior=False)  # priors stay with numpyro's sample sites
+    _handles[key] = lk
+    while len(_handles) > MAX_CACHED_DATASETS:
+        _, old = _handles.popitem(last=False)
+        old.close()
+    return lk
+
+
+def close_datasets():
+    """Free every cached packed dataset (HBM) -- call after the last fit on a dataset."""
+    while _handles:
+        _, lk = _handles.popitem()
+        lk.close()
 
 
 occu = _drop_in("occu")

@@ -20,17 +20,31 @@ class NutsSampler:
                  num_samples: int = 1000, *, seed: int = 0, init_params: Optional[np.ndarray] = None,
                  init_radius: float = 2.0, max_tree_depth: int = 10, target_accept_prob: float = 0.8,
                  step_size: float = 1.0, adapt_step_size: bool = True, adapt_mass_matrix: bool = True,
-                 find_heuristic_step_size: bool = False):
+                 find_heuristic_step_size: bool = False, validate_init: bool = True):
         self._lib = _lib.load()
         self.lk = likelihood
         self.num_chains, self.num_warmup, self.num_samples = int(num_chains), int(num_warmup), int(num_samples)
         D = likelihood.theta_dim
-        if init_params is None:  # init_to_uniform(radius=2), fit.py:93
+        drawn = init_params is None
+        if drawn:  # init_to_uniform(radius=2), fit.py:93
             rng = np.random.default_rng(seed)
             init_params = rng.uniform(-init_radius, init_radius, size=(num_chains, D))
         th0 = np.ascontiguousarray(init_params, dtype=likelihood.np_dtype)
         if th0.shape != (num_chains, D):
             raise ValueError(f"init_params must have shape ({num_chains}, {D})")
+        # numpyro's find_valid_initial_params: a start whose log-density or gradient is not finite is redrawn
+        # (up to 100 times); a chain started there would reject every proposal and return identical draws
+        if validate_init:
+            for attempt in range(101):
+                lp, gr = likelihood.logp_and_grad(th0)
+                bad = ~(np.isfinite(lp) & np.isfinite(gr).all(axis=1))
+                if not bad.any():
+                    break
+                if not drawn or attempt == 100:
+                    raise _lib.BiolithB200Error(
+                        -1, "NutsSampler", f"log-density or gradient is not finite at the initial position of chain(s) "
+                        f"{np.flatnonzero(bad)[:8].tolist()}")
+                th0[bad] = rng.uniform(-init_radius, init_radius, size=(int(bad.sum()), D))
         cfg = bl_nuts_config(
             n_chains=num_chains, num_warmup=num_warmup, num_samples=num_samples, max_tree_depth=max_tree_depth,
             adapt_step_size=int(adapt_step_size), adapt_mass_matrix=int(adapt_mass_matrix),
@@ -53,6 +67,12 @@ class NutsSampler:
             n = min(chunk, budget)
             check(self._lib.bl_nuts_run(self._h, n, poll_every, C.byref(steps), C.byref(done)), "bl_nuts_run")
             budget -= n
+            # site-sharded handles: a peer that timed out in the fused exchange leaves stale sums behind
+            err = C.c_int32(0)
+            check(self._lib.bl_dataset_comm_error(self.lk.handle, C.byref(err)), "bl_dataset_comm_error")
+            if err.value:
+                raise _lib.BiolithB200Error(-4, "bl_nuts_run", "a peer rank timed out in the cross-GPU exchange; "
+                                            "the sampler state is not trustworthy")
             if done.value >= self.num_chains:
                 break
             if timeout is not None and time.perf_counter() - t0 > timeout:
