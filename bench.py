@@ -404,7 +404,8 @@ def main():
 # They turn a measured time into an achieved issue / SFU rate; the peaks are measured by bl_pipe_peak.
 PROFILED = {
     # workload: (warp-instructions per (unit, chain) x 32 lanes -> per lane, MUFU per (unit, chain), DRAM bytes / launch, source)
-    "occu_1m_x8_c1024": dict(instr=270.0, mufu=30.0, traffic=236_505_600, src="profiles/r01_occu_chain_v6.txt"),
+    # K1d (csrc/occu_signed.cu): 293.30 MB read + 6.99 MB written per launch (signed records: 176 MB packed)
+    "occu_1m_x8_c1024": dict(instr=190.7, mufu=18.1, traffic=300_288_512, src="profiles/r02_occu_signed_v2.txt"),
     "occu_cop_500k_x12": dict(instr=368.0, mufu=44.0, traffic=None, src="profiles/r01_occu_cop_chain_v1.txt"),
     "occu_rn_200k_x10_k50": dict(instr=14886.0, mufu=None, traffic=None, src="profiles/r01_occu_rn_chain_v2.txt"),
 }
@@ -442,8 +443,8 @@ def rooflines(lib, device, workload, model, lk, X, W, chains, ms_launch, args):
                    "pass over the data); with tile reuse across the chain batch frac > 1 is expected and is NOT a "
                    "physical bandwidth"}
     prof = PROFILED.get(workload)
-    chain_kernel = (prof is not None and args.dtype == "float32" and not args.strict_math and chains >= 32
-                    and lk.kernel_variant == 1)
+    chain_kernel = (prof is not None and args.dtype == "float32" and not args.strict_math
+                    and chains >= (64 if model == "occu_cs" else 32))
     if chain_kernel:
         pk = pipe_peaks(lib, device)
         winstr = prof["instr"] * units * chains  # warp-instructions x lanes... = thread-instructions

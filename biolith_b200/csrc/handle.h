@@ -14,7 +14,8 @@ struct Plan {
   int nch;           // site-parallel engine: chains interleaved per pass over a warp-tile
   int chain_variant; // BL_CHAIN_VARIANT as read when the plan was made
   int chain_bt;      // threads per block of the lane = chain variant (occu: 128 or 256)
-  int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel; 2 / 3 / 4: occu_rn / occu_cop / occu_cs lane=chain kernels
+  int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel (K1c); 2 / 3 / 4: occu_rn / occu_cop / occu_cs lane=chain
+                     // kernels; 5: occu lane=chain kernel over signed records (K1d, occu_signed.cu)
 };
 }  // namespace bl
 
@@ -26,6 +27,8 @@ struct bl_dataset {
   size_t smem_limit = 0;
   void* packed = nullptr;
   size_t packed_bytes = 0;
+  void* packed_signed = nullptr;  // occu fp32 without extras: AoS signed site records for K1d (occu_signed.cu)
+  size_t packed_signed_bytes = 0;
   double cop_const = 0.0;
   int64_t n_masked = 0;
   // fp64 block partials [nsplit][C][NQ], per-chunk tickets, raw sums for the collective path

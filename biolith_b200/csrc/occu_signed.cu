@@ -1,0 +1,427 @@
+// K1d: lane = chain occu kernel over SIGNED site records (fp32, no false-positive extras, C >= 32).
+//
+// Same mapping as K1c (occu_chain.cu): lane = chain, every lane reads the same site (broadcast LDS.128),
+// block = <= 256 chains x a contiguous range of 32-site tiles staged by TMA (cp.async.bulk) through an
+// mbarrier ring, fp32 inside a tile, fp64 across tiles / blocks, ticketed last-block reduction.
+// What changes is the arithmetic per visit (reference: biolith/models/occu.py:221-242 with p_fp = z p):
+//
+//   sgn_j = +1 (detection), -1 (non-detection), 0 (masked);  v_j = sgn_j * [1, W_j]  (packed once per fit)
+//   x'_j  = v_j . alpha                      the Bernoulli log-lik of visit j is  log sigmoid(x'_j) = -log(1 + e_j),
+//   e_j   = exp(-x'_j)                       and d/d alpha = q_j v_j with q_j = e_j / (1 + e_j)
+//
+//   * ONE ex2 per visit (alpha is pre-scaled by -log2 e per chain, so x2 = v . alpha2 feeds ex2 directly);
+//   * product-log:  sum_j log(1 + e_j) = log prod_j (1 + e_j)   -> one lg2 per 4 visits;
+//   * batch inversion: 1 / (1 + e_j) for 4 visits from ONE rcp of their product (+ Newton) and 8 multiplies;
+//   * masked / padded visits have v = 0 -> e = 1, 1 + e = 2 exactly -> they add exactly 1 to the lg2 sum, which the
+//     per-site count `cnt` removes again, and nothing to the gradient: no mask handling in the loop.
+//   => 17 MUFU and ~190 instructions per (site, chain) at J = 8, Ko = 3 instead of 30 and 270 (K1c).
+//
+// numpyro's clamp_probs (p~ = clip(p, tiny, 1 - eps), zero gradient outside) is kept EXACTLY: the fast form is only
+// valid while no visit is clamped at the low side, i.e. while every 1 + e_j < 2^23 (x > log((1-eps)/eps) for a
+// non-detection; the bound is conservative for detections, whose clamp sits at log tiny).  Each lane tracks the
+// largest pair product (>= every 1 + e_j of the pair); lanes over the bound take the per-visit clamped form of
+// K1c for that site (slow_visits: bit-identical arithmetic to sfu::softsig<true>), selected per lane, so a chain's
+// result never depends on its neighbours.  The high-side clamp changes a visit by < 1.2e-7 absolute in value and
+// gradient (log(1 - eps) vs -log(1 + e), e < eps) -- below the fp32 rounding of the O(1) terms it is added to.
+// The site-level terms (psi, logaddexp over z) keep sfu::softsig<true> as in K1c.
+#include <cstdlib>
+
+#include "engine.cuh"
+
+namespace bl {
+
+constexpr int kSignedMaxKs = 8;
+
+// record of one unit, floats:  [ X (XR = roundup(Ks,4)) | n1, cnt, valid, 0 | NQ quads x 4 visits x VR ]
+struct SignedLayout {
+  int ks, ko, J;
+  int XR, VR, nq, R;
+  int G;  // warp-tiles (32 sites each) staged per TMA / ring slot: fewer block barriers per site
+  int64_t n_units, n_tiles;
+};
+
+// Sites staged per ring slot.  Measured on B200 (config 2, ms per 1024-chain evaluation; block barrier per slot):
+// 32 sites 7.57 | 64: 7.39 | 128: 7.32 | 256: 8.30 (ring too shallow) -> the largest group whose slot stays <= 24 KB.
+static int signed_group(int R) {
+  if (const char* e = getenv("BL_SIGNED_G")) {  // tuning switch, read when a launch is configured
+    const int g = atoi(e);
+    if (g == 1 || g == 2 || g == 4 || g == 8) return g;
+  }
+  int g = 4;
+  while (g > 1 && (size_t)R * kWarp * g * sizeof(float) > 24576) g /= 2;
+  return g;
+}
+
+__host__ __device__ inline int signed_vr(int ko) { return ko + 1 <= 2 ? 2 : (ko + 1 <= 4 ? 4 : 8); }
+
+inline SignedLayout make_signed_layout(const Layout& L) {
+  SignedLayout s{};
+  s.ks = L.ks; s.ko = L.ko; s.J = L.J;
+  s.XR = (L.ks + 3) / 4 * 4;
+  s.VR = signed_vr(L.ko);
+  s.nq = (L.J + 3) / 4;
+  s.R = s.XR + 4 + s.nq * 4 * s.VR;
+  s.n_units = L.n_units;
+  s.n_tiles = L.n_tiles_padded;  // padded to 8 warp-tiles, so any group size up to 8 stays in bounds
+  s.G = signed_group(s.R);
+  return s;
+}
+
+__global__ void repack_signed_kernel(const float* __restrict__ packed, float* __restrict__ out, Layout L,
+                                     SignedLayout S) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= S.n_tiles * kWarp) return;
+  float* rec = out + u * (int64_t)S.R;
+  for (int i = 0; i < S.R; ++i) rec[i] = 0.f;
+  float* hdr = rec + S.XR;
+  if (u >= L.n_units) {  // padding unit of the last tile: weight 0, every visit "masked"
+    hdr[1] = (float)(4 * S.nq);
+    return;
+  }
+  const float* base = packed + (u / kWarp) * (int64_t)L.F * kWarp + (u % kWarp);
+  for (int k = 0; k < L.ks; ++k) rec[k] = base[k * kWarp];
+  int cnt = 4 * S.nq - L.J;
+  float* vis = hdr + 4;
+  for (int j = 0; j < L.J; ++j) {
+    const uint32_t yw = __float_as_uint(base[(L.off_y + (j >> 5)) * kWarp]);
+    const uint32_t mw = __float_as_uint(base[(L.off_m + (j >> 5)) * kWarp]);
+    const bool m = (mw >> (j & 31)) & 1u, y = (yw >> (j & 31)) & 1u;
+    const float sgn = m ? (y ? 1.f : -1.f) : 0.f;
+    cnt += m ? 0 : 1;
+    vis[j * S.VR] = sgn;
+    for (int k = 0; k < L.ko; ++k) vis[j * S.VR + 1 + k] = sgn * base[(L.off_w + j * L.ko + k) * kWarp];
+  }
+  hdr[0] = base[L.off_n1 * kWarp];
+  hdr[1] = (float)cnt;
+  hdr[2] = 1.f;
+}
+
+cudaError_t launch_repack_signed(const void* packed, void* out, const Layout& L, cudaStream_t st) {
+  const SignedLayout S = make_signed_layout(L);
+  const int64_t n = S.n_tiles * kWarp;
+  if (n == 0) return cudaSuccess;
+  repack_signed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)packed, (float*)out, L, S);
+  return cudaGetLastError();
+}
+
+size_t occu_signed_bytes(const Layout& L) {
+  const SignedLayout S = make_signed_layout(L);
+  return (size_t)S.n_tiles * kWarp * S.R * sizeof(float);
+}
+
+// ---- exact per-visit form for lanes with a clamped visit (rare): K1c's arithmetic on the signed record ----------
+template <int KO> struct SlowOut { float L1; float ga[KO + 1]; };
+
+template <int KO>
+__device__ __noinline__ SlowOut<KO> slow_visits(const float* __restrict__ vis, int nvis,
+                                               const float* __restrict__ alpha) {
+  constexpr int VR = KO + 1 <= 2 ? 2 : (KO + 1 <= 4 ? 4 : 8);
+  SlowOut<KO> o;
+  o.L1 = 0.f;
+#pragma unroll
+  for (int k = 0; k <= KO; ++k) o.ga[k] = 0.f;
+  for (int j = 0; j < nvis; ++j) {
+    const float* v = vis + j * VR;
+    const float sgn = v[0];
+    if (sgn == 0.f) continue;
+    float xp = sgn * alpha[0];
+#pragma unroll
+    for (int k = 0; k < KO; ++k) xp = fmaf(v[1 + k], alpha[1 + k], xp);
+    const float x = sgn * xp;  // = alpha0 + W . alpha, bit-identical to K1c's fma chain (sgn = +-1 is exact)
+    const float yf = sgn > 0.f ? 1.f : 0.f;
+    const sfu::SoftSig ss = sfu::softsig<true>(x);
+    o.L1 += fmaf(yf, ss.xc, -ss.s);
+    const float g = ss.inr ? (yf - ss.p) : 0.f;
+    const float gs = g * sgn;  // d/d alpha_k = g W_k = (g sgn) v_k
+#pragma unroll
+    for (int k = 0; k <= KO; ++k) o.ga[k] = fmaf(gs, v[k], o.ga[k]);
+  }
+  return o;
+}
+
+constexpr float kClampProduct = 8388608.0f;  // 2^23 > (1 - eps) / eps: a pair product below it has no clamped visit
+
+template <int N> struct LoadVec {
+  static __device__ __forceinline__ void ld(const float* p, float (&o)[N]) {
+    static_assert(N % 4 == 0 || N == 2, "records are float4 / float2 multiples");
+    if constexpr (N == 2) {
+      const float2 t = *reinterpret_cast<const float2*>(p);
+      o[0] = t.x; o[1] = t.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < N / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+        o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+      }
+    }
+  }
+};
+
+// KS < 0: runtime Ks (<= kSignedMaxKs); NQD = 0: runtime number of visit quads.
+// Tried and rejected (measured, config 2): a dedicated producer warp with full / empty mbarrier pairs instead of
+// the block barrier per ring slot (288 threads -> 96..112 registers): 7.76 ms against 7.32 ms; three resident
+// blocks per SM (72..80 registers, spills): 8.2 ms.
+template <int KS, int KO, int NQD, int NS, int MINB, int BT>
+__global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams p, const SignedLayout S) {
+  constexpr int KSM = KS < 0 ? kSignedMaxKs : KS;
+  constexpr int KB = KSM + 1, KA = KO + 1, NQ = 1 + KB + KA;
+  constexpr int VR = KO + 1 <= 2 ? 2 : (KO + 1 <= 4 ? 4 : 8);
+  constexpr int XRC = (KSM + 3) / 4 * 4;
+  const int ks = KS < 0 ? S.ks : KS;
+  const int XR = KS < 0 ? S.XR : XRC;
+  const int nq = NQD > 0 ? NQD : S.nq;
+  const int R = (KS >= 0 && NQD > 0) ? (XRC + 4 + NQD * 4 * VR) : S.R;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
+  __shared__ int s_is_last;
+  const int TS = S.G * kWarp;  // sites per stage
+  const uint32_t tile_elems = (uint32_t)R * TS;
+  const uint32_t tile_bytes = tile_elems * sizeof(float);
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.y * p.CB;
+  const int ncb = min(p.CB, p.C - c0);
+  const bool chain_ok = tid < ncb;
+  const bool warp_on = (tid & ~31) < ncb;
+  const int64_t nbt = p.n_block_tiles;
+  const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
+  const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
+  const int n_it = (int)(bt_end - bt_begin);
+  const float* packed = reinterpret_cast<const float*>(p.packed);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nstage; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * p.D;
+  float b[KB], a2[KA];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) b[k] = (k <= ks) ? th[k] : 0.f;
+#pragma unroll
+  for (int k = 0; k < KA; ++k) a2[k] = th[ks + 1 + k] * -sfu::kLog2e;  // ex2(v . a2) = exp(-x')
+  const float* th_alpha = th + ks + 1;
+  double* g64 = reinterpret_cast<double*>(stage0 + (size_t)p.nstage * tile_elems) + tid;
+  double logp64 = 0.0;
+#pragma unroll
+  for (int i = 1; i < NQ; ++i) g64[(size_t)i * BT] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    const int pre = min(p.nstage, n_it);
+    for (int s = 0; s < pre; ++s) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + s) * tile_elems, tile_bytes,
+                    &bars[s]);
+    }
+  }
+  const float log_tiny = Num<float>::log_tiny();
+
+  for (int it = 0; it < n_it; ++it) {
+    const int s = it % p.nstage;
+    mbar_wait(&bars[s], (uint32_t)((it / p.nstage) & 1));
+    const float* tile = stage0 + (size_t)s * tile_elems;
+    const int64_t unit0 = (bt_begin + it) * TS;
+    const int n_valid = (int)max((int64_t)0, min((int64_t)TS, S.n_units - unit0));
+    float acc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = 0.f;
+    if (warp_on) {
+      for (int g0 = 0; g0 < n_valid; g0 += NS) {
+        const float* rec = tile + (size_t)g0 * R;
+        float lgsum[NS], mx[NS], ga[KA][NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          lgsum[i] = 0.f; mx[i] = 0.f;
+#pragma unroll
+          for (int k = 0; k < KA; ++k) ga[k][i] = 0.f;
+        }
+#pragma unroll(NQD > 0 ? NQD : 1)
+        for (int q = 0; q < nq; ++q) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            float v[4 * VR];
+            LoadVec<4 * VR>::ld(rec + (size_t)i * R + XR + 4 + q * 4 * VR, v);
+            float e[4], u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x2 = v[j * VR] * a2[0];
+#pragma unroll
+              for (int k = 0; k < KO; ++k) x2 = fmaf(v[j * VR + 1 + k], a2[1 + k], x2);
+              e[j] = sfu::ex2(x2);
+              u[j] = 1.0f + e[j];
+            }
+            const float p12 = u[0] * u[1], p34 = u[2] * u[3], pp = p12 * p34;
+            mx[i] = fmaxf(mx[i], fmaxf(p12, p34));
+            float rinv = sfu::rcp(pp);
+            rinv = fmaf(rinv, fmaf(-pp, rinv, 1.0f), rinv);  // Newton: MUFU.RCP's bias would add up over 10^7 visits
+            lgsum[i] += sfu::lg2(pp);
+            const float r12 = rinv * p34, r34 = rinv * p12;  // 1 / (u0 u1), 1 / (u2 u3)
+            const float qv[4] = {e[0] * (r12 * u[1]), e[1] * (r12 * u[0]), e[2] * (r34 * u[3]), e[3] * (r34 * u[2])};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int k = 0; k < KA; ++k) ga[k][i] = fmaf(qv[j], v[j * VR + k], ga[k][i]);
+            }
+          }
+        }
+        float L1[NS], n1[NS], vf[NS];
+        bool slow = false;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          const float4 h = *reinterpret_cast<const float4*>(rec + (size_t)i * R + XR);
+          n1[i] = h.x; vf[i] = h.z;
+          L1[i] = -sfu::kLn2 * (lgsum[i] - h.y);
+          slow |= mx[i] >= kClampProduct;
+        }
+        if (__any_sync(0xffffffffu, slow)) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            const SlowOut<KO> so = slow_visits<KO>(rec + (size_t)i * R + XR + 4, 4 * nq, th_alpha);
+            if (mx[i] >= kClampProduct) {
+              L1[i] = so.L1;
+#pragma unroll
+              for (int k = 0; k < KA; ++k) ga[k][i] = so.ga[k];
+            }
+          }
+        }
+        float eta[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) eta[i] = b[0];
+#pragma unroll
+        for (int k4 = 0; k4 < XRC; k4 += 4) {
+          if (k4 < ks) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              const float4 x = *reinterpret_cast<const float4*>(rec + (size_t)i * R + k4);
+              eta[i] = fmaf(x.x, b[1 + k4], eta[i]);
+              if (k4 + 1 < KSM) eta[i] = fmaf(x.y, b[2 + k4 < KB ? 2 + k4 : 0], eta[i]);
+              if (k4 + 2 < KSM) eta[i] = fmaf(x.z, b[3 + k4 < KB ? 3 + k4 : 0], eta[i]);
+              if (k4 + 3 < KSM) eta[i] = fmaf(x.w, b[4 + k4 < KB ? 4 + k4 : 0], eta[i]);
+            }
+          }
+        }
+        float geta[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          const sfu::SoftSig se = sfu::softsig<true>(eta[i]);
+          const float av = (se.xc - se.s) + L1[i];      // log psi~ + L1
+          const float bv = n1[i] * log_tiny - se.s;     // log1p(-psi~) + L0   (L0 = n1 log tiny)
+          const float d = av - bv;
+          const float td = sfu::ex2(-fabsf(d) * sfu::kLog2e);
+          const float ud = 1.0f + td;
+          float invd = sfu::rcp(ud);
+          invd = fmaf(invd, fmaf(-ud, invd, 1.0f), invd);
+          const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
+          const float r = rr * vf[i];
+          const float ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv)) * vf[i];
+          geta[i] = se.inr ? (rr - se.p) * vf[i] : 0.f;
+          logp64 += (double)ell;  // fp64 per unit: NUTS needs energy *differences* of a ~1e6-sized sum
+          acc[1] += geta[i];
+#pragma unroll
+          for (int k = 0; k < KA; ++k) acc[1 + KB + k] = fmaf(r, ga[k][i], acc[1 + KB + k]);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < XRC; k4 += 4) {
+          if (k4 < ks) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              const float4 x = *reinterpret_cast<const float4*>(rec + (size_t)i * R + k4);
+              acc[2 + k4] = fmaf(geta[i], x.x, acc[2 + k4]);
+              if (k4 + 1 < KSM) acc[3 + k4 < NQ ? 3 + k4 : 0] = fmaf(geta[i], x.y, acc[3 + k4 < NQ ? 3 + k4 : 0]);
+              if (k4 + 2 < KSM) acc[4 + k4 < NQ ? 4 + k4 : 0] = fmaf(geta[i], x.z, acc[4 + k4 < NQ ? 4 + k4 : 0]);
+              if (k4 + 3 < KSM) acc[5 + k4 < NQ ? 5 + k4 : 0] = fmaf(geta[i], x.w, acc[5 + k4 < NQ ? 5 + k4 : 0]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 1; i < NQ; ++i) g64[(size_t)i * BT] += (double)acc[i];
+    __syncthreads();
+    if (tid == 0 && it + p.nstage < n_it) {
+      mbar_expect_tx(&bars[s], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + it + p.nstage) * tile_elems,
+                    tile_bytes, &bars[s]);
+    }
+  }
+  if (chain_ok) {
+    double* my = p.partial + ((size_t)blockIdx.x * p.C + c0 + tid) * p.NQ;
+    my[0] = logp64;
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+      if (k <= ks) my[1 + k] = g64[(size_t)(1 + k) * BT];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) my[2 + ks + k] = g64[(size_t)(1 + KB + k) * BT];
+  }
+  finish_block<float>(p, c0, ncb, &s_is_last);
+}
+
+template <int KS, int KO, int NQD, int NS, int MINB, int BT>
+static cudaError_t launch_signed_one(const EvalParams& p, const SignedLayout& S, dim3 grid, size_t smem,
+                                     cudaStream_t st, int* occ) {
+  auto kern = occu_signed_kernel<KS, KO, NQD, NS, MINB, BT>;
+  constexpr int NT = BT;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, NT, smem);
+  kern<<<grid, NT, smem, st>>>(p, S);
+  return cudaGetLastError();
+}
+
+bool occu_signed_supported(int dtype, int ks, int ko, uint32_t flags) {
+  if (dtype != BL_F32) return false;
+  if (flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) return false;
+  return ks >= 0 && ks <= kSignedMaxKs && ko >= 1 && ko <= 4;
+}
+
+int64_t occu_signed_block_tiles(const Layout& L) {
+  const SignedLayout S = make_signed_layout(L);
+  return (L.n_tiles + S.G - 1) / S.G;
+}
+
+size_t occu_signed_smem(const Layout& L, int nstage, int block_threads) {
+  const SignedLayout S = make_signed_layout(L);
+  size_t b = 128 + (size_t)nstage * S.R * kWarp * S.G * sizeof(float);
+  b = (b + 15) & ~size_t(15);
+  return b + (size_t)(3 + kSignedMaxKs + L.ko) * block_threads * sizeof(double);  // fp64 gradient columns
+}
+
+// same rule as K1c (occu_chain_block_threads): 256-thread blocks on whole multiples of 256 chains, else 128
+int occu_signed_block_threads(int C) {
+  if (const char* e = getenv("BL_SIGNED_BT")) return atoi(e) == 128 ? 128 : 256;
+  return (C > 0 && C % 256 == 0) ? 256 : 128;
+}
+
+static int signed_ns() {
+  const char* e = getenv("BL_SIGNED_NS");  // tuning switch, read when a launch is configured
+  return e ? atoi(e) : 0;
+}
+
+template <int KS, int KO, int NQD>
+static cudaError_t launch_signed_bt(const EvalParams& p, const SignedLayout& S, dim3 grid, size_t smem,
+                                    cudaStream_t st, int* occ) {
+  const int ns = signed_ns();
+  if (p.chain_bt == 128) {
+    if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 4, 128>(p, S, grid, smem, st, occ);
+    return launch_signed_one<KS, KO, NQD, 2, 4, 128>(p, S, grid, smem, st, occ);
+  }
+  if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 2, 256>(p, S, grid, smem, st, occ);
+  return launch_signed_one<KS, KO, NQD, 2, 2, 256>(p, S, grid, smem, st, occ);
+}
+
+cudaError_t launch_occu_signed(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
+  const SignedLayout S = make_signed_layout(p.L);
+  const int ks = p.L.ks, ko = p.L.ko;
+  if (ks == 5 && ko == 3 && S.nq == 2) return launch_signed_bt<5, 3, 2>(p, S, grid, smem, st, occ);
+  if (ks == 1 && ko == 1) return launch_signed_bt<1, 1, 0>(p, S, grid, smem, st, occ);
+  if (ko == 1) return launch_signed_bt<-1, 1, 0>(p, S, grid, smem, st, occ);
+  if (ko == 2) return launch_signed_bt<-1, 2, 0>(p, S, grid, smem, st, occ);
+  if (ko == 3) return launch_signed_bt<-1, 3, 0>(p, S, grid, smem, st, occ);
+  if (ko == 4) return launch_signed_bt<-1, 4, 0>(p, S, grid, smem, st, occ);
+  return cudaErrorNotSupported;
+}
+
+}  // namespace bl
