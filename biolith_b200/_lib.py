@@ -95,6 +95,8 @@ SIGNATURES = {
     "bl_stream_sync": (C.c_int, [_P]),
     "bl_flush_l2": (C.c_int, [C.c_int32, _P]),
     "bl_pipe_peak": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "bl_mufu_error": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int64, C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -41,6 +41,43 @@ __global__ void __launch_bounds__(kMbThreads) issue_bench_kernel(float* out, flo
   if (s == 12345.678f) out[0] = s;
 }
 
+// Error statistics of the MUFU approximations the fp32 kernels use, against double-precision references:
+// which = 0: ex2.approx(x), relative error; 1: lg2.approx(x), absolute error; 2: rcp.approx + one Newton step,
+// relative error.  x uniform on [lo, hi]; out = {sum err, sum err^2, max |err|} (double atomics).
+__global__ void mufu_error_kernel(int which, float lo, float hi, long long n, double* out) {
+  double s1 = 0.0, s2 = 0.0, mx = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = lo + (hi - lo) * (float)((double)(i + 0.5) / (double)n);
+    float y;
+    double ref, err;
+    if (which == 0) {
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+      ref = exp2((double)x);
+      err = ((double)y - ref) / ref;
+    } else if (which == 1) {
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+      ref = log2((double)x);
+      err = (double)y - ref;
+    } else {
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+      y = fmaf(y, fmaf(-x, y, 1.0f), y);
+      ref = 1.0 / (double)x;
+      err = ((double)y - ref) / ref;
+    }
+    s1 += err; s2 += err * err; mx = fmax(mx, fabs(err));
+  }
+  atomicAdd(&out[0], s1);
+  atomicAdd(&out[1], s2);
+  // max via CAS on the bit pattern (non-negative doubles order like integers)
+  unsigned long long* m = reinterpret_cast<unsigned long long*>(&out[2]);
+  unsigned long long v = (unsigned long long)__double_as_longlong(mx), old = *m;
+  while (v > old) {
+    const unsigned long long prev = atomicCAS(m, old, v);
+    if (prev == old) break;
+    old = prev;
+  }
+}
+
 }  // namespace bl
 
 #define CU_TRY(expr)                                                                              \
@@ -85,6 +122,25 @@ BL_API int bl_pipe_peak(int32_t device, int32_t which, double* per_second, doubl
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(d_out);
+  return BL_OK;
+}
+
+BL_API int bl_mufu_error(int32_t device, int32_t which, float lo, float hi, int64_t n, double* mean, double* rms,
+                         double* max_abs) {
+  using namespace bl;
+  if (which < 0 || which > 2 || n < 1 || !mean || !rms || !max_abs) return fail(BL_ERR_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(device));
+  double* d_out = nullptr;
+  CU_TRY(cudaMalloc(&d_out, 3 * sizeof(double)));
+  CU_TRY(cudaMemset(d_out, 0, 3 * sizeof(double)));
+  mufu_error_kernel<<<592, 256>>>(which, lo, hi, (long long)n, d_out);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  double h[3];
+  CU_TRY(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d_out);
+  *mean = h[0] / (double)n;
+  *rms = sqrt(h[1] / (double)n);
+  *max_abs = h[2];
   return BL_OK;
 }
 

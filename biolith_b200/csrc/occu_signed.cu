@@ -9,7 +9,12 @@
 //   x'_j  = v_j . alpha                      the Bernoulli log-lik of visit j is  log sigmoid(x'_j) = -log(1 + e_j),
 //   e_j   = exp(-x'_j)                       and d/d alpha = q_j v_j with q_j = e_j / (1 + e_j)
 //
-//   * ONE ex2 per visit (alpha is pre-scaled by -log2 e per chain, so x2 = v . alpha2 feeds ex2 directly);
+//   * ONE ex2 per visit: the covariate slots of a record hold sgn W * (-log2 e), rounded per element at pack time, and
+//     the intercept enters as sgn * (A_hi + A_lo) with A = -log2(e) alpha_0 split into two floats per chain, so
+//     x2 = -log2(e) x' feeds ex2 directly.  (Near the posterior mode |g| << |H| |theta|: evaluating the density at a
+//     theta that is off by a FIXED relative 1e-8 -- a rounded log2 e, a rounded alpha_0 log2 e -- is by itself a
+//     gradient error of 4e-6 .. 1.5e-5 of |g|inf at config 2, measured; per-element rounding of the data is
+//     unbiased noise and does not add up.)
 //   * product-log:  sum_j log(1 + e_j) = log prod_j (1 + e_j)   -> one lg2 per 4 visits;
 //   * batch inversion: 1 / (1 + e_j) for 4 visits from ONE rcp of their product (+ Newton) and 8 multiplies;
 //   * masked / padded visits have v = 0 -> e = 1, 1 + e = 2 exactly -> they add exactly 1 to the lg2 sum, which the
@@ -31,6 +36,17 @@
 namespace bl {
 
 constexpr int kSignedMaxKs = 8;
+
+constexpr double kLog2eD = 1.4426950408889634074, kLn2D = 0.6931471805599453094;
+constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - (float)log2(e): second term of the two-float constant
+constexpr float kLn2Lo = -1.9046542121259336e-09f;  // ln(2)   - (float)ln(2)
+
+// 2^(t log2 e) with the two-float constant: the argument carries no fixed relative error
+__device__ __forceinline__ float exp_neg_abs(float x) {
+  const float t = -fabsf(x);
+  return sfu::ex2(fmaf(t, kLog2eLo, t * sfu::kLog2e));
+}
+
 
 // record of one unit, floats:  [ X (XR = roundup(Ks,4)) | n1, cnt, valid, 0 | NQ quads x 4 visits x VR ]
 struct SignedLayout {
@@ -88,8 +104,10 @@ __global__ void repack_signed_kernel(const float* __restrict__ packed, float* __
     const bool m = (mw >> (j & 31)) & 1u, y = (yw >> (j & 31)) & 1u;
     const float sgn = m ? (y ? 1.f : -1.f) : 0.f;
     cnt += m ? 0 : 1;
+    // slot 0: sgn (exact); covariates: sgn W * (-log2 e), rounded once per element (unbiased)
     vis[j * S.VR] = sgn;
-    for (int k = 0; k < L.ko; ++k) vis[j * S.VR + 1 + k] = sgn * base[(L.off_w + j * L.ko + k) * kWarp];
+    for (int k = 0; k < L.ko; ++k)
+      vis[j * S.VR + 1 + k] = (float)(-kLog2eD * (double)(sgn * base[(L.off_w + j * L.ko + k) * kWarp]));
   }
   hdr[0] = base[L.off_n1 * kWarp];
   hdr[1] = (float)cnt;
@@ -121,18 +139,19 @@ __device__ __noinline__ SlowOut<KO> slow_visits(const float* __restrict__ vis, i
 #pragma unroll
   for (int k = 0; k <= KO; ++k) o.ga[k] = 0.f;
   for (int j = 0; j < nvis; ++j) {
-    const float* v = vis + j * VR;
+    const float* v = vis + j * VR;  // = [sgn, -log2(e) sgn W_j]
     const float sgn = v[0];
     if (sgn == 0.f) continue;
-    float xp = sgn * alpha[0];
+    float x2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < KO; ++k) xp = fmaf(v[1 + k], alpha[1 + k], xp);
-    const float x = sgn * xp;  // = alpha0 + W . alpha, bit-identical to K1c's fma chain (sgn = +-1 is exact)
+    for (int k = 0; k < KO; ++k) x2 = fmaf(v[1 + k], alpha[1 + k], x2);
+    const float xp = fmaf(sgn, alpha[0], -fmaf(x2, kLn2Lo, x2 * sfu::kLn2));  // x' = sgn (alpha0 + W . alpha)
+    const float x = sgn * xp;
     const float yf = sgn > 0.f ? 1.f : 0.f;
     const sfu::SoftSig ss = sfu::softsig<true>(x);
     o.L1 += fmaf(yf, ss.xc, -ss.s);
     const float g = ss.inr ? (yf - ss.p) : 0.f;
-    const float gs = g * sgn;  // d/d alpha_k = g W_k = (g sgn) v_k
+    const float gs = g * sgn;  // d/d alpha_k = g W_k; kept in the record's units: (g sgn) v_k = -log2(e) g W_k, k >= 1
 #pragma unroll
     for (int k = 0; k <= KO; ++k) o.ga[k] = fmaf(gs, v[k], o.ga[k]);
   }
@@ -156,6 +175,55 @@ template <int N> struct LoadVec {
     }
   }
 };
+
+// NV = 4 or 8 visits of one site: x2 = v . a2, e = 2^x2, u = 1 + e; ONE lg2 and ONE rcp (+ Newton) for the product of
+// all NV factors (batch inversion through the pair-product tree), q_j = e_j / u_j, ga += q_j v_j.  `mx` tracks the
+// largest pair product: while it stays below 2^23 no visit is clamped and the product of 8 factors is < 2^92.
+template <int KO, int NV>
+__device__ __forceinline__ void visit_block(const float* __restrict__ vp, const float (&a2)[KO + 2], float& lgsum,
+                                            float& mx, float (&ga)[KO + 1]) {
+  constexpr int VR = KO + 1 <= 2 ? 2 : (KO + 1 <= 4 ? 4 : 8);
+  static_assert(NV == 4 || NV == 8, "visits are processed in quads or octets");
+  float v[NV * VR];
+  LoadVec<NV * VR>::ld(vp, v);
+  float e[NV], u[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float x2 = v[j * VR] * a2[KO + 1];  // sgn * A_lo
+#pragma unroll
+    for (int k = 0; k < KO; ++k) x2 = fmaf(v[j * VR + 1 + k], a2[1 + k], x2);
+    x2 = fmaf(v[j * VR], a2[0], x2);    // + sgn * A_hi
+    e[j] = sfu::ex2(x2);
+    u[j] = 1.0f + e[j];
+  }
+  float pr[NV / 2], rp[NV / 2];  // pair products and their reciprocals
+#pragma unroll
+  for (int i = 0; i < NV / 2; ++i) pr[i] = u[2 * i] * u[2 * i + 1];
+  if constexpr (NV == 4) {
+    const float pp = pr[0] * pr[1];
+    mx = fmaxf(mx, fmaxf(pr[0], pr[1]));
+    float rinv = sfu::rcp(pp);
+    rinv = fmaf(rinv, fmaf(-pp, rinv, 1.0f), rinv);  // Newton: MUFU.RCP's bias would add up over 10^7 visits
+    lgsum += sfu::lg2(pp);
+    rp[0] = rinv * pr[1];
+    rp[1] = rinv * pr[0];
+  } else {
+    const float pa = pr[0] * pr[1], pb = pr[2] * pr[3], pp = pa * pb;
+    mx = fmaxf(fmaxf(mx, fmaxf(pr[0], pr[1])), fmaxf(pr[2], pr[3]));
+    float rinv = sfu::rcp(pp);
+    rinv = fmaf(rinv, fmaf(-pp, rinv, 1.0f), rinv);
+    lgsum += sfu::lg2(pp);
+    const float ra = rinv * pb, rb = rinv * pa;  // 1 / (u0 u1 u2 u3), 1 / (u4 u5 u6 u7)
+    rp[0] = ra * pr[1]; rp[1] = ra * pr[0];
+    rp[2] = rb * pr[3]; rp[3] = rb * pr[2];
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float qj = e[j] * (rp[j / 2] * u[j ^ 1]);  // e_j / u_j
+#pragma unroll
+    for (int k = 0; k <= KO; ++k) ga[k] = fmaf(qj, v[j * VR + k], ga[k]);
+  }
+}
 
 // KS < 0: runtime Ks (<= kSignedMaxKs); NQD = 0: runtime number of visit quads.
 // Tried and rejected (measured, config 2): a dedicated producer warp with full / empty mbarrier pairs instead of
@@ -194,11 +262,16 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
     fence_mbar_init();
   }
   const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * p.D;
-  float b[KB], a2[KA];
+  float b[KB], a2[KA + 1];
 #pragma unroll
   for (int k = 0; k < KB; ++k) b[k] = (k <= ks) ? th[k] : 0.f;
 #pragma unroll
-  for (int k = 0; k < KA; ++k) a2[k] = th[ks + 1 + k] * -sfu::kLog2e;  // ex2(v . a2) = exp(-x')
+  for (int k = 1; k < KA; ++k) a2[k] = th[ks + 1 + k];  // covariate slots of the records are pre-scaled by -log2(e)
+  {
+    const double A = -kLog2eD * (double)th[ks + 1];  // intercept: two floats, no per-chain rounding of -log2(e) alpha_0
+    a2[0] = (float)A;
+    a2[KA] = (float)(A - (double)a2[0]);
+  }
   const float* th_alpha = th + ks + 1;
   double* g64 = reinterpret_cast<double*>(stage0 + (size_t)p.nstage * tile_elems) + tid;
   double logp64 = 0.0;
@@ -227,40 +300,28 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
     if (warp_on) {
       for (int g0 = 0; g0 < n_valid; g0 += NS) {
         const float* rec = tile + (size_t)g0 * R;
-        float lgsum[NS], mx[NS], ga[KA][NS];
+        float lgsum[NS], mx[NS], ga[NS][KA];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
           lgsum[i] = 0.f; mx[i] = 0.f;
 #pragma unroll
-          for (int k = 0; k < KA; ++k) ga[k][i] = 0.f;
+          for (int k = 0; k < KA; ++k) ga[i][k] = 0.f;
         }
-#pragma unroll(NQD > 0 ? NQD : 1)
-        for (int q = 0; q < nq; ++q) {
+        if constexpr (NQD == 2) {  // 8 visits: one octet per site
 #pragma unroll
-          for (int i = 0; i < NS; ++i) {
-            float v[4 * VR];
-            LoadVec<4 * VR>::ld(rec + (size_t)i * R + XR + 4 + q * 4 * VR, v);
-            float e[4], u[4];
+          for (int i = 0; i < NS; ++i)
+            visit_block<KO, 8>(rec + (size_t)i * R + XR + 4, a2, lgsum[i], mx[i], ga[i]);
+        } else {
+          int q = 0;
+          for (; q + 1 < nq; q += 2) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x2 = v[j * VR] * a2[0];
+            for (int i = 0; i < NS; ++i)
+              visit_block<KO, 8>(rec + (size_t)i * R + XR + 4 + q * 4 * VR, a2, lgsum[i], mx[i], ga[i]);
+          }
+          if (q < nq) {
 #pragma unroll
-              for (int k = 0; k < KO; ++k) x2 = fmaf(v[j * VR + 1 + k], a2[1 + k], x2);
-              e[j] = sfu::ex2(x2);
-              u[j] = 1.0f + e[j];
-            }
-            const float p12 = u[0] * u[1], p34 = u[2] * u[3], pp = p12 * p34;
-            mx[i] = fmaxf(mx[i], fmaxf(p12, p34));
-            float rinv = sfu::rcp(pp);
-            rinv = fmaf(rinv, fmaf(-pp, rinv, 1.0f), rinv);  // Newton: MUFU.RCP's bias would add up over 10^7 visits
-            lgsum[i] += sfu::lg2(pp);
-            const float r12 = rinv * p34, r34 = rinv * p12;  // 1 / (u0 u1), 1 / (u2 u3)
-            const float qv[4] = {e[0] * (r12 * u[1]), e[1] * (r12 * u[0]), e[2] * (r34 * u[3]), e[3] * (r34 * u[2])};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-              for (int k = 0; k < KA; ++k) ga[k][i] = fmaf(qv[j], v[j * VR + k], ga[k][i]);
-            }
+            for (int i = 0; i < NS; ++i)
+              visit_block<KO, 4>(rec + (size_t)i * R + XR + 4 + q * 4 * VR, a2, lgsum[i], mx[i], ga[i]);
           }
         }
         float L1[NS], n1[NS], vf[NS];
@@ -279,7 +340,7 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
             if (mx[i] >= kClampProduct) {
               L1[i] = so.L1;
 #pragma unroll
-              for (int k = 0; k < KA; ++k) ga[k][i] = so.ga[k];
+              for (int k = 0; k < KA; ++k) ga[i][k] = so.ga[k];
             }
           }
         }
@@ -302,22 +363,32 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
         float geta[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-          const sfu::SoftSig se = sfu::softsig<true>(eta[i]);
-          const float av = (se.xc - se.s) + L1[i];      // log psi~ + L1
-          const float bv = n1[i] * log_tiny - se.s;     // log1p(-psi~) + L0   (L0 = n1 log tiny)
-          const float d = av - bv;
-          const float td = sfu::ex2(-fabsf(d) * sfu::kLog2e);
+          // psi~ = sigmoid(xc) with xc the clamped eta (numpyro's clamp_probs in logit space, see sfu::softsig);
+          // a = log psi~ + L1, b = log(1 - psi~) + n1 log tiny share the term -softplus(xc) = -max(xc,0) - log u_e, so
+          //   d = a - b = xc + L1 - n1 log tiny,   logaddexp(a, b) = max(d, 0) + n1 log tiny - max(xc, 0) + log(u_d / u_e)
+          const float xc = fminf(fmaxf(eta[i], sfu::kXLo), sfu::kXHi);
+          const bool inr = xc == eta[i];
+          const float te = exp_neg_abs(xc);
+          const float ue = 1.0f + te;
+          float inve = sfu::rcp(ue);
+          inve = fmaf(inve, fmaf(-ue, inve, 1.0f), inve);
+          const float psi = (xc >= 0.f) ? inve : te * inve;
+          const float bl = n1[i] * log_tiny;
+          const float al = xc + L1[i];
+          const float d = al - bl;
+          const float td = exp_neg_abs(d);
           const float ud = 1.0f + td;
           float invd = sfu::rcp(ud);
           invd = fmaf(invd, fmaf(-ud, invd, 1.0f), invd);
           const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
           const float r = rr * vf[i];
-          const float ell = fmaf(sfu::lg2(ud), sfu::kLn2, fmaxf(av, bv)) * vf[i];
-          geta[i] = se.inr ? (rr - se.p) * vf[i] : 0.f;
+          // max(a, b) picked by select, not as b + max(d, 0): n1 log tiny ~ -87 n1 would cost the sum its low bits
+          const float ell = (fmaf(sfu::lg2(ud * inve), sfu::kLn2, (d >= 0.f ? al : bl) - fmaxf(xc, 0.f))) * vf[i];
+          geta[i] = inr ? (rr - psi) * vf[i] : 0.f;
           logp64 += (double)ell;  // fp64 per unit: NUTS needs energy *differences* of a ~1e6-sized sum
           acc[1] += geta[i];
 #pragma unroll
-          for (int k = 0; k < KA; ++k) acc[1 + KB + k] = fmaf(r, ga[k][i], acc[1 + KB + k]);
+          for (int k = 0; k < KA; ++k) acc[1 + KB + k] = fmaf(r, ga[i][k], acc[1 + KB + k]);
         }
 #pragma unroll
         for (int k4 = 0; k4 < XRC; k4 += 4) {
@@ -335,7 +406,9 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
       }
     }
 #pragma unroll
-    for (int i = 1; i < NQ; ++i) g64[(size_t)i * BT] += (double)acc[i];
+    for (int i = 1; i <= KB + 1; ++i) g64[(size_t)i * BT] += (double)acc[i];
+#pragma unroll
+    for (int i = 2 + KB; i < NQ; ++i) g64[(size_t)i * BT] += (double)acc[i] * -kLn2D;  // covariate slots carry -log2(e)
     __syncthreads();
     if (tid == 0 && it + p.nstage < n_it) {
       mbar_expect_tx(&bars[s], tile_bytes);
@@ -408,6 +481,7 @@ static cudaError_t launch_signed_bt(const EvalParams& p, const SignedLayout& S, 
     if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 4, 128>(p, S, grid, smem, st, occ);
     return launch_signed_one<KS, KO, NQD, 2, 4, 128>(p, S, grid, smem, st, occ);
   }
+  // measured (config 2 near the mode, ms): two sites interleaved 7.34, one 7.75
   if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 2, 256>(p, S, grid, smem, st, occ);
   return launch_signed_one<KS, KO, NQD, 2, 2, 256>(p, S, grid, smem, st, occ);
 }

@@ -235,6 +235,66 @@ def test_config2_full_size_against_c_oracle():
         np.testing.assert_allclose(np.concatenate([gr_a, gr_b]), gr, rtol=1e-5, atol=1e-5 * np.abs(gr).max())
 
 
+@pytest.mark.parametrize("missing", [False, True])
+def test_config2_full_size_near_the_mode(missing):
+    """Config 2 (and its simulate_missing=True variant) with the chains where NUTS spends its time:
+    within 2e-3 of the simulating truth, where |g|inf ~ 2e3 is tiny against sum |terms| ~ 3e5 and against
+    |H| |theta| ~ 1e6 -- any fixed relative error in an internal constant shows up here first.  Both math modes
+    must stay within 1e-5 of the fp64 C oracle (gradient relative to |g|inf)."""
+    import biolith_b200 as bb
+    from biolith_b200.simulate import simulate_occupancy
+    from oracle import c_oracle
+
+    data, true = simulate_occupancy("occu", n_site_covs=5, n_obs_covs=3, n_sites=1_000_000,
+                                    deployment_days_per_site=56, random_seed=0, simulate_missing=missing)
+    X, W, y = (data[k].astype(np.float32) for k in ("site_covs", "obs_covs", "obs"))
+    truth = np.concatenate([true["beta"][0], true["alpha"][0]])
+    rng = np.random.default_rng(0)
+    th = (truth + 2e-3 * rng.standard_normal((256, 10))).astype(np.float32)
+    idx = list(range(0, 256, 16))
+    ref_lp, ref_gr = c_oracle.occu_logp_grad(th[idx].astype(np.float64), X.astype(np.float64), W.astype(np.float64),
+                                             y.astype(np.float64), dtype=np.float64, nthreads=0)
+    assert np.abs(ref_gr).max() < 2e-2 * 3e5, "the chains are meant to sit near the mode"
+    for kw in ({}, dict(strict_math=True)):
+        with bb.OccupancyLikelihood("occu", X, W, y, max_chains=256, **kw) as lk:
+            from oracle import occupancy as orc
+
+            assert np.array_equal(lk.mask(), orc.expected_mask(X, W, y)[0]), "NaN mask is not bit-exact at full size"
+            lp, gr = lk.logp_and_grad(th)
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"config2 near mode missing={missing} {kw}")
+
+
+@pytest.mark.parametrize("model,sim_kw,model_kw,okw", [
+    ("occu_rn", dict(n_sites=200_000, deployment_days_per_site=70), dict(max_abundance=50), dict(max_abundance=50)),
+    ("occu_cop", dict(n_sites=500_000, deployment_days_per_site=84, simulate_missing=True),
+     dict(false_positives_constant=True), dict(fp_constant=True)),
+])
+def test_configs_3_and_4_full_size_against_c_oracle(model, sim_kw, model_kw, okw):
+    """BASELINE configs[2] (occu_rn 200k x 10, K = 50) and configs[3] (occu_cop 500k x 12, NaN-masked) at FULL size:
+    a sample of the chains of a 256-chain batch (the lane = chain kernels) against the C/OpenMP oracle in double
+    arithmetic, at U(-2,2) (init_to_uniform) and near the simulating truth."""
+    import biolith_b200 as bb
+    from biolith_b200.simulate import simulate_occupancy
+    from oracle import c_oracle
+
+    data, true = simulate_occupancy(model, n_site_covs=5, n_obs_covs=3, random_seed=0, **sim_kw)
+    X, W, y = (data[k].astype(np.float32) for k in ("site_covs", "obs_covs", "obs"))
+    T = data.get("session_duration")
+    T = None if T is None else T.astype(np.float32)
+    rng = np.random.default_rng(5)
+    truth = np.concatenate([true["beta"][0], true["alpha"][0]])
+    with bb.OccupancyLikelihood(model, X, W, y, T, max_chains=256, **model_kw) as lk:
+        D = lk.theta_dim
+        t0 = np.concatenate([truth, np.full(D - truth.size, np.log(0.1))])
+        th = np.concatenate([rng.uniform(-2, 2, size=(128, D)), t0 + 1e-2 * rng.standard_normal((128, D))]).astype(np.float32)
+        lp, gr = lk.logp_and_grad(th)
+    idx = [0, 77, 127, 128, 200, 255]
+    fn = c_oracle.occu_rn_logp_grad if model == "occu_rn" else c_oracle.occu_cop_logp_grad
+    args = (X, W, y) if model == "occu_rn" else (X, W, y, T)
+    ref_lp, ref_gr = fn(th[idx].astype(np.float64), *args, **okw)
+    assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"{model} full size")
+
+
 @pytest.mark.parametrize("name", ["occu_5x3", "occu_missing", "rn_5x3", "cop_missing_5x3", "nmix_missing_5x3",
                                   "nmix_default", "cs_missing_5x3", "cs_default"])
 def test_strict_math_flag(name):
