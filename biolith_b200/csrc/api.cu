@@ -58,6 +58,12 @@ int occu_signed_block_threads(int C);
 int64_t occu_signed_block_tiles(const Layout& L);
 cudaError_t launch_repack_signed(const void* packed, void* out, const Layout& L, cudaStream_t st);
 cudaError_t launch_occu_signed(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
+bool occu_rn2_supported(int dtype, int ks, int ko, int J, int K, uint32_t flags);
+size_t occu_rn2_bytes(const Layout& L);
+size_t occu_rn2_smem(const Layout& L, int nstage, int K, int bt);
+int occu_rn2_block_threads(const Layout& L, int C, int K, size_t smem_limit);
+cudaError_t launch_repack_rn2(const void* packed, void* out, const Layout& L, cudaStream_t st);
+cudaError_t launch_occu_rn2(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 bool occu_rn_chain_supported(int dtype, int ks, int ko, uint32_t flags);
 int occu_rn_chain_block_threads(int C);
 size_t occu_rn_chain_smem(const Layout& L, int nstage, int K, int D, int bt);
@@ -161,6 +167,9 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
         occu_rn_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags) &&
         occu_rn_chain_smem(ds->L, 2, ds->desc.max_abundance, ds->D, occu_rn_chain_block_threads(C)) <= ds->smem_limit)
       pl.chain_kernel = 2;
+    if (want_chain && ds->desc.model == BL_MODEL_OCCU_RN && ds->packed_rn2 &&
+        occu_rn2_smem(ds->L, 2, ds->desc.max_abundance, 128) <= ds->smem_limit)
+      pl.chain_kernel = 6;
     if (want_chain && ds->desc.model == BL_MODEL_OCCU_COP &&
         occu_cop_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
       pl.chain_kernel = 3;
@@ -171,6 +180,7 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
       const int bt = pl.chain_kernel == 1   ? occu_chain_block_threads(ds->L.ks, ds->L.ko, C)
                      : pl.chain_kernel == 5 ? occu_signed_block_threads(C)
+                     : pl.chain_kernel == 6 ? occu_rn2_block_threads(ds->L, C, ds->desc.max_abundance, ds->smem_limit)
                      : pl.chain_kernel == 2 ? occu_rn_chain_block_threads(C)
                      : pl.chain_kernel == 3 ? occu_cop_chain_block_threads(C)
                                             : occu_cs_chain_block_threads(C);  // chains per block
@@ -187,6 +197,11 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
         pl.g.n_block_tiles = occu_signed_block_tiles(ds->L);  // groups of warp-tiles per ring slot
         while (pl.g.nstage > 2 && occu_signed_smem(ds->L, pl.g.nstage, bt) > ds->smem_limit * bt / 512) --pl.g.nstage;
         pl.g.smem_bytes = occu_signed_smem(ds->L, pl.g.nstage, bt);
+      } else if (pl.chain_kernel == 6) {
+        const size_t budget = bt == 256 ? ds->smem_limit / 2 : ds->smem_limit / 3;
+        while (pl.g.nstage > 2 && occu_rn2_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, bt) > budget) --pl.g.nstage;
+        pl.g.smem_bytes = occu_rn2_smem(ds->L, pl.g.nstage, ds->desc.max_abundance, bt);
+        pl.rn_global = false;
       } else if (pl.chain_kernel == 3) {
         pl.g.smem_bytes = occu_cop_chain_smem(ds->L, pl.g.nstage, bt);
       } else if (pl.chain_kernel == 4) {
@@ -210,6 +225,7 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     int occ = 0;
     cudaError_t e = pl.chain_kernel == 1   ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 5 ? launch_occu_signed(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                    : pl.chain_kernel == 6 ? launch_occu_rn2(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 2 ? launch_occu_rn_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 3 ? launch_occu_cop_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 4 ? launch_occu_cs_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
@@ -290,8 +306,10 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
   p.rn_scratch_global = pl->rn_global ? ds->rn_scratch : nullptr;
   const dim3 grid(pl->g.nsplit, pl->g.n_chunks);
   if (pl->chain_kernel == 5) p.packed = ds->packed_signed;
+  if (pl->chain_kernel == 6) p.packed = ds->packed_rn2;
   cudaError_t e = pl->chain_kernel == 1   ? launch_occu_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 5 ? launch_occu_signed(p, grid, pl->g.smem_bytes, st, nullptr)
+                  : pl->chain_kernel == 6 ? launch_occu_rn2(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 2 ? launch_occu_rn_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 3 ? launch_occu_cop_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 4 ? launch_occu_cs_chain(p, grid, pl->g.smem_bytes, st, nullptr)
@@ -428,6 +446,14 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
         CU_BRK(launch_repack_signed(ds->packed, ds->packed_signed, L, nullptr));
         g_launches.fetch_add(1);
       }
+      if (d->model == BL_MODEL_OCCU_RN && !ds->force_engine &&
+          occu_rn2_supported(d->dtype, L.ks, L.ko, L.J, d->max_abundance, d->flags)) {
+        // second packing for the lane = chain kernel K2d: visits sorted detections-first (occu_rn2.cu)
+        ds->packed_rn2_bytes = occu_rn2_bytes(L);
+        CU_BRK(cudaMalloc(&ds->packed_rn2, ds->packed_rn2_bytes));
+        CU_BRK(launch_repack_rn2(ds->packed, ds->packed_rn2, L, nullptr));
+        g_launches.fetch_add(1);
+      }
       CU_BRK(cudaDeviceSynchronize());
     }
     int h_err = 0;
@@ -486,7 +512,7 @@ int bl_dataset_destroy(bl_dataset* ds) {
   if (!ds) return BL_OK;
   cudaSetDevice(ds->desc.device);
   comm_destroy(ds);
-  cudaFree(ds->packed); cudaFree(ds->packed_signed); cudaFree(ds->partial); cudaFree(ds->counters); cudaFree(ds->sums);
+  cudaFree(ds->packed); cudaFree(ds->packed_signed); cudaFree(ds->packed_rn2); cudaFree(ds->partial); cudaFree(ds->counters); cudaFree(ds->sums);
   cudaFree(ds->rn_scratch);
   cudaFree(ds->d_theta); cudaFree(ds->d_out);
   if (ds->h_theta) cudaFreeHost(ds->h_theta);

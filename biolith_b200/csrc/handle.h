@@ -15,7 +15,8 @@ struct Plan {
   int chain_variant; // BL_CHAIN_VARIANT as read when the plan was made
   int chain_bt;      // threads per block of the lane = chain variant (occu: 128 or 256)
   int chain_kernel;  // 0: site-parallel engine; 1: occu lane=chain kernel (K1c); 2 / 3 / 4: occu_rn / occu_cop / occu_cs lane=chain
-                     // kernels; 5: occu lane=chain kernel over signed records (K1d, occu_signed.cu)
+                     // kernels; 5: occu lane=chain kernel over signed records (K1d, occu_signed.cu); 6: occu_rn lane=chain
+                     // kernel in probability space over sorted records (K2d, occu_rn2.cu)
 };
 }  // namespace bl
 
@@ -29,6 +30,8 @@ struct bl_dataset {
   size_t packed_bytes = 0;
   void* packed_signed = nullptr;  // occu fp32 without extras: AoS signed site records for K1d (occu_signed.cu)
   size_t packed_signed_bytes = 0;
+  void* packed_rn2 = nullptr;     // occu_rn fp32 without extras: visits sorted detections-first for K2d (occu_rn2.cu)
+  size_t packed_rn2_bytes = 0;
   double cop_const = 0.0;
   int64_t n_masked = 0;
   // fp64 block partials [nsplit][C][NQ], per-chunk tickets, raw sums for the collective path
