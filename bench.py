@@ -209,8 +209,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"], help="site-sharded cross-rank sum")
-    ap.add_argument("--nuts-warmup", type=int, default=200)
-    ap.add_argument("--nuts-samples", type=int, default=100)
+    ap.add_argument("--nuts-warmup", type=int, default=0,
+                    help="default: 1000 at N = 1 (the metric's own schedule, fit.py:22-23), 300 at N > 1")
+    ap.add_argument("--nuts-samples", type=int, default=0, help="default: as --nuts-warmup")
     ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s section")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the configs[2]/[3] lines (N=1)")
     ap.add_argument("--no-site-sharded", action="store_true", help="skip the configs[4] block (N>1)")
@@ -220,6 +221,11 @@ def main():
                          "(SURVEY 8d asks for both; the kernels have no theta-dependent branches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    n_ranks = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.nuts_warmup <= 0:
+        args.nuts_warmup = 1000 if n_ranks == 1 else 300
+    if args.nuts_samples <= 0:
+        args.nuts_samples = 1000 if n_ranks == 1 else 300
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -610,6 +616,7 @@ def run_nuts(args, lk, chains, rank, world, shard, dist):
     r = s.results()
     s.close()
     local = dict(samples=r["samples"], leapfrogs=r["leapfrogs"], warmup_leapfrogs=r["warmup_leapfrogs"],
+                 rows=np.array([r["rows_evaluated"]]),
                  num_steps=r["num_steps"], accept_prob=r["accept_prob"], diverging=r["diverging"],
                  step_size=r["step_size"], wall=np.array([wall]), steps=np.array([r["global_steps"]]),
                  ok=np.array([ok]))
@@ -633,7 +640,10 @@ def run_nuts(args, lk, chains, rank, world, shard, dist):
         "wall_s": wall, "complete": bool(np.all(g["ok"])), "global_steps": int(np.max(g["steps"])),
         "ms_per_global_step": 1e3 * wall / max(int(np.max(g["steps"])), 1),
         "leapfrogs_per_chain_mean": float(leaps.mean()), "leapfrogs_per_draw": float(g["num_steps"].mean()),
-        "useful_eval_frac": float(leaps.sum() / (x.shape[0] * max(int(np.max(g["steps"])), 1))) if shard == "chains"
+        # leapfrogs used by the chains / chain-evaluations spent (finished chains are compacted away in whole warps)
+        "useful_eval_frac": float(leaps.sum() / max(float(np.sum(g["rows"])), 1.0)) if shard == "chains"
+        else float(leaps.sum() / max(float(np.max(g["rows"])), 1.0)),
+        "lockstep_eval_frac": float(leaps.sum() / (x.shape[0] * max(int(np.max(g["steps"])), 1))) if shard == "chains"
         else float(leaps.mean() / max(int(np.max(g["steps"])), 1)),
         "accept_prob_mean": float(g["accept_prob"].mean()), "divergence_frac": float(g["diverging"].mean()),
         "step_size_median": float(np.median(g["step_size"])),

@@ -76,6 +76,7 @@ SIGNATURES = {
     "bl_nuts_create": (C.c_int, [_P, C.POINTER(bl_nuts_config), _P, C.POINTER(_P)]),
     "bl_nuts_run": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bl_nuts_get": (C.c_int, [_P] * 11),
+    "bl_nuts_rows_evaluated": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bl_nuts_destroy": (C.c_int, [_P]),
     "bl_comm_unique_id": (C.c_int, [_P, C.c_size_t]),
     "bl_dataset_attach_nccl": (C.c_int, [_P, _P, C.c_size_t, C.c_int32, C.c_int32]),

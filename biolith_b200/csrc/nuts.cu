@@ -550,6 +550,7 @@ struct bl_nuts {
   cudaGraphExec_t graph_exec = nullptr;
   int graph_steps = 0;
   int n_rows = 0;          // current evaluation batch (active chains rounded up to a chain chunk)
+  int64_t rows_evaluated = 0;  // sum over global steps of the batch size actually evaluated (after compaction)
   bool compaction = true;
 };
 
@@ -715,6 +716,7 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
       int rc = one_step();
       if (rc) return rc;
       ++n;
+      s->rows_evaluated += s->n_rows;
       capture();
       need_capture = false;
     }
@@ -722,10 +724,12 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
       CU_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
       g_launches.fetch_add(2 * (int64_t)s->graph_steps);
       n += s->graph_steps;
+      s->rows_evaluated += (int64_t)s->graph_steps * s->n_rows;
     } else {
       for (int k = 0; k < poll_every && n < max_steps; ++k, ++n) {
         int rc = one_step();
         if (rc) return rc;
+        s->rows_evaluated += s->n_rows;
       }
     }
     CU_TRY(cudaGetLastError());
@@ -751,6 +755,12 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
   s->steps += n;
   if (steps_done) *steps_done = s->steps;
   if (chains_done) *chains_done = done;
+  return BL_OK;
+}
+
+int bl_nuts_rows_evaluated(bl_nuts* s, int64_t* rows) {
+  if (!s || !rows) return fail(BL_ERR_INVALID, "NULL argument");
+  *rows = s->rows_evaluated;
   return BL_OK;
 }
 

@@ -219,7 +219,7 @@ __device__ __forceinline__ bool rn2_site_fast(const float* __restrict__ vis, flo
   constexpr int ND = N1 > 0 ? N1 : 1;
   float q[ND], r[ND], qk[ND], P0[ND], G[ND];
   float u2[JT];  // log2(1 - r_j) of the non-detections; 0 for detections and masked visits (neutral)
-  float U2 = 0.f, umin = 0.f;
+  float U2 = 0.f, umin = 0.f, rmin = 1.0f;
 #pragma unroll
   for (int j = 0; j < JT; ++j) {
     float w[VR];
@@ -232,6 +232,7 @@ __device__ __forceinline__ bool rn2_site_fast(const float* __restrict__ vis, flo
     if (j < N1) {
       q[j] = qj; r[j] = rj; qk[j] = 1.0f; P0[j] = 0.f; G[j] = 0.f;
       u2[j] = 0.f;
+      rmin = fminf(rmin, rj);
     } else {
       const float mx0 = fmaxf(nu, 0.f);
       float l2q = -(fmaf(mx0, kL2eLo, mx0 * sfu::kLog2e) + sfu::lg2(uj));  // log2(1 - r) = -softplus(nu) log2 e
@@ -241,6 +242,8 @@ __device__ __forceinline__ bool rn2_site_fast(const float* __restrict__ vis, flo
       umin = fminf(umin, l2q);
     }
   }
+  // rmin < 1e-30: a detection that is all but impossible -> the exact log-space form decides (checked at the end:
+  // every lane has to reach the warp-wide reduction below)
   const float Kf = (float)K;
   const float eta2 = fmaf(eta, kL2eLo, eta * sfu::kLog2e);
   const float etaU = eta2 + U2;
@@ -256,45 +259,56 @@ __device__ __forceinline__ bool rn2_site_fast(const float* __restrict__ vis, flo
   // ---- pre-pass: centred joint exponent Jc_k = (k - k0) etaU - (G_k - G_k0) + clamp corrections, its maximum
   float M = -Num<float>::inf();
   {
-    float kf = 0.f;
+    float kf = 0.f, dk = -k0f;
+    float* ck = col;
     int k = 0;
     for (; k <= kfree; ++k) {
-      const float jc = fmaf(kf - k0f, etaU, Gk0 - sG[k]);
+      const float jc = fmaf(dk, etaU, Gk0 - sG[k]);
       M = fmaxf(M, jc);
-      col[(size_t)k * BT] = jc;
-      kf += 1.0f;
+      *ck = jc;
+      ck += BT; dk += 1.0f;
     }
+    kf = (float)k;
     for (; k <= K; ++k) {
       float corr = 0.f;
 #pragma unroll
       for (int j = N1; j < JT; ++j) corr += fmaxf(fmaf(-kf, u2[j], kL2Eps), 0.f);
-      const float jc = fmaf(kf - k0f, etaU, Gk0 - sG[k]) + corr;
+      const float jc = fmaf(dk, etaU, Gk0 - sG[k]) + corr;
       M = fmaxf(M, jc);
-      col[(size_t)k * BT] = jc;
-      kf += 1.0f;
+      *ck = jc;
+      ck += BT; dk += 1.0f; kf += 1.0f;
     }
   }
-  // ---- main pass
-  float Z = 0.f, Zp = 0.f, Ep = 0.f, S = 0.f;
+  // ---- main pass.  State 0 is peeled: every detection factor is clip(0) = tiny there and it carries no gradient
+  // (k = 0); from k = 1 on P_k >= r_j > tiny (the caller's guard), so only the upper clamp remains in the loop.
+  float Z, Zp, Ep = 0.f, S = 0.f;
   {
-    float kf = 0.f;
-    for (int k = 0; k <= K; ++k) {
-      const float W0 = sfu::ex2(col[(size_t)k * BT] - M);
-      const float pw = sfu::ex2(fmaf(kf - k0pf, eta2, Gk0p - sG[k]));
+    float W = sfu::ex2(col[0] - M);
+#pragma unroll
+    for (int j = 0; j < N1; ++j) W *= FLT_MIN;
+    Z = W;
+    Zp = sfu::ex2(fmaf(-k0pf, eta2, Gk0p - sG[0]));
+    col[0] = 0.f;
+#pragma unroll
+    for (int j = 0; j < N1; ++j) { P0[j] = r[j]; qk[j] = q[j]; }
+    float kf = 1.0f, dkp = 1.0f - k0pf;
+    float* ck = col + BT;
+    for (int k = 1; k <= K; ++k) {
+      const float W0 = sfu::ex2(*ck - M);
+      const float pw = sfu::ex2(fmaf(dkp, eta2, Gk0p - sG[k]));
       Zp += pw;
       Ep = fmaf(kf, pw, Ep);
-      float F[ND], pre[ND];
-#pragma unroll
-      for (int j = 0; j < N1; ++j) F[j] = fminf(fmaxf(P0[j], FLT_MIN), kOneMinusEps);  // clip(1 - q^k, tiny, 1 - eps)
-      float W = W0;
+      W = W0;
       if constexpr (N1 > 0) {
+        float F[ND], pre[ND];
+#pragma unroll
+        for (int j = 0; j < N1; ++j) F[j] = fminf(P0[j], kOneMinusEps);  // clip(1 - q^k, tiny, 1 - eps), k >= 1
         pre[0] = F[0];
 #pragma unroll
         for (int j = 1; j < N1; ++j) pre[j] = pre[j - 1] * F[j];
         W = W0 * pre[N1 - 1];
         // weight without visit j: prefix * suffix (no division)
-        const float kW0 = kf * W0;
-        float suf = kW0;
+        float suf = kf * W0;
 #pragma unroll
         for (int j = N1 - 1; j >= 0; --j) {
           const float others = j > 0 ? pre[j - 1] * suf : suf;
@@ -310,11 +324,11 @@ __device__ __forceinline__ bool rn2_site_fast(const float* __restrict__ vis, flo
       }
       Z += W;
       S = fmaf(kf, W, S);
-      col[(size_t)k * BT] = S;
-      kf += 1.0f;
+      *ck = S;
+      ck += BT; kf += 1.0f; dkp += 1.0f;
     }
   }
-  if (!(Z > 1e-25f) || !(Z < 1e30f) || !(Zp > 0.f)) return false;
+  if (!(Z > 1e-25f) || !(Z < 1e30f) || !(Zp > 0.f) || rmin < 1e-30f) return false;
   const float iZ = sfu::rcp(Z), iZp = sfu::rcp(Zp);
   // constants of the two centred exponents (one double FMA pair per unit): cJ - cP
   const double cdiff = ((double)k0f * (double)etaU - (double)Gk0) - ((double)k0pf * (double)eta2 - (double)Gk0p);
@@ -521,11 +535,12 @@ size_t occu_rn2_smem(const Layout& L, int nstage, int K, int bt) {
   return b + (size_t)(K + 1) * sizeof(float) + 16;            // log2 Gamma table
 }
 
-// threads (= chains) per block: 256 when two such blocks fit an SM's shared memory, else 128
+// threads (= chains) per block.  Measured on B200 (config 3, K = 50, 256 chains, ms per evaluation): 128 threads
+// (167 registers, no spills, 3 blocks / SM) 9.08, 256 threads (128 registers, spills in the wide instantiations) 9.30
 int occu_rn2_block_threads(const Layout& L, int C, int K, size_t smem_limit) {
-  if (const char* e = getenv("BL_RN2_BT")) return atoi(e) == 128 ? 128 : 256;
-  if (C <= 128 || (C % 256 != 0 && C < 512)) return 128;
-  return occu_rn2_smem(L, 2, K, 256) * 2 <= smem_limit ? 256 : 128;
+  (void)L; (void)C; (void)K; (void)smem_limit;
+  if (const char* e = getenv("BL_RN2_BT")) return atoi(e) == 256 ? 256 : 128;
+  return 128;
 }
 
 static cudaError_t ensure_rn2_tables() {

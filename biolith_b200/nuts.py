@@ -97,7 +97,10 @@ class NutsSampler:
             self._h, samples.ctypes.data, acc.ctypes.data, nsteps.ctypes.data, div.ctypes.data, pe.ctypes.data,
             eps.ctypes.data, imm.ctypes.data, leaps.ctypes.data, wleaps.ctypes.data, saved.ctypes.data),
             "bl_nuts_get")
+        rows = C.c_int64(0)
+        check(self._lib.bl_nuts_rows_evaluated(self._h, C.byref(rows)), "bl_nuts_rows_evaluated")
         return dict(
+            rows_evaluated=int(rows.value),
             samples=samples.transpose(1, 0, 2), accept_prob=acc.T, num_steps=nsteps.T, diverging=div.T.astype(bool),
             potential_energy=pe.T, step_size=eps, inverse_mass_matrix=imm.T, leapfrogs=leaps,
             warmup_leapfrogs=wleaps, n_saved=saved, global_steps=self.steps, wall_s=self.wall_s)
