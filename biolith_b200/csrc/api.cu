@@ -118,6 +118,8 @@ static void fill_params(const bl_dataset* ds, EvalParams& p) {
   p.prior_fp_b = ds->desc.prior_fp_b;
   p.prior_fp_rate = ds->desc.prior_fp_rate;
   p.nch = 4;
+  p.coop_reduce = 1;
+  if (const char* ev = getenv("BL_COOP_REDUCE")) p.coop_reduce = atoi(ev) != 0;
 }
 
 // geometry for C chains (cached); grows the fp64 partial workspace when needed
@@ -404,7 +406,9 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
   if (e != cudaSuccess) { delete ds; return fail(BL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
   ds->num_sms = prop.multiProcessorCount;
-  ds->smem_limit = prop.sharedMemPerBlockOptin - 1024;  // minus the kernels' static shared memory
+  // per-block budget for DYNAMIC shared memory: minus the kernels' static part (s_is_last, the 512-byte staging of the
+  // final reduction) and the 1 KB the driver reserves per block, so that limit / n blocks really are resident
+  ds->smem_limit = prop.sharedMemPerBlockOptin - 4096;
 
   const Layout& L = ds->L;
   const size_t es = elem_size(d->dtype), ds_in = elem_size(d->data_dtype);

@@ -132,13 +132,40 @@ __device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int nc
   __syncthreads();
   if (!*s_is_last) return;
   __threadfence();
-  for (int i = tid; i < ncb * NQ; i += blockDim.x) {
-    double total = 0.0;
-    const double* src = p.partial + (size_t)c0 * NQ + i;
-    for (unsigned int b = 0; b < gridDim.x; ++b) total += __ldcg(src + (size_t)b * p.C * NQ);
-    const int c = c0 + i / NQ, q = i % NQ;
-    if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
-    else finalize_chain<T>(p, c, q, total, true);
+  const int items = ncb * NQ;
+  // measured (config 2, us per evaluation, thread-per-item / warp-per-item): C=1 (11 items) 45.8 / 41.6, C=2 63.4 / 63.1,
+  // C=4 (44 items) 90.1 / 99.5, C=5 110.6 / 126.5 -> cooperative only up to 32 items
+  constexpr int kCoopItems = 32;
+  __shared__ double s_tot[kCoopItems];
+  if (items <= kCoopItems && p.coop_reduce) {
+    // Few items (small chain batches): one WARP per (chain, quantity) -- the lanes sum the site splits b = lane,
+    // lane + 32, ... and a fixed xor-butterfly adds the 32 partial sums (a fixed order: deterministic), so the
+    // splits' L2 round trips overlap instead of queueing behind one thread; then one THREAD per item adds the
+    // priors (fp64 log / lgamma) and writes the outputs.
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < items; j += nwarps) {
+      double total = 0.0;
+      const double* src = p.partial + (size_t)c0 * NQ + j;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) total += __ldcg(src + (size_t)b * p.C * NQ);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (lane == 0) s_tot[j] = total;
+    }
+    __syncthreads();
+    if (tid < items) {
+      const int c = c0 + tid / NQ, q = tid % NQ;
+      if (p.allreduce) p.sums[(size_t)c * NQ + q] = s_tot[tid] + (q == 0 ? p.cop_const : 0.0);
+      else finalize_chain<T>(p, c, q, s_tot[tid], true);
+    }
+  } else {
+    for (int i = tid; i < items; i += blockDim.x) {
+      double total = 0.0;
+      const double* src = p.partial + (size_t)c0 * NQ + i;
+      for (unsigned int b = 0; b < gridDim.x; ++b) total += __ldcg(src + (size_t)b * p.C * NQ);
+      const int c = c0 + i / NQ, q = i % NQ;
+      if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
+      else finalize_chain<T>(p, c, q, total, true);
+    }
   }
   if (tid == 0) p.counters[blockIdx.y] = 0;  // self-reset for the next launch
 }
@@ -162,6 +189,10 @@ __device__ __forceinline__ void reduce_into(const T* __restrict__ q, bool valid,
   }
 }
 
+// Tried and rejected for small chain batches (measured, config 2): per-lane fp32 running sums [chain][q][thread] in
+// shared memory with one butterfly per 32 tiles instead of one per (warp-tile, chain): 11 shared-memory
+// read-modify-writes per (tile, chain) cost more than the 16-shuffle transposed butterfly they replace and shorten
+// the TMA ring (C = 5: 130 us against 112 us, C = 8: 182 against 154, C = 1 unchanged).
 template <typename T, class Model, int MINB>
 __global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
