@@ -15,6 +15,7 @@ BL_ABI_VERSION = 1
 BL_MODEL = {"occu": 0, "occu_rn": 1, "occu_cop": 2, "nmixture": 3, "occu_cs": 4}
 BL_F32, BL_F64 = 0, 1
 BL_FLAG_FP_CONSTANT, BL_FLAG_FP_UNOCCUPIED, BL_FLAG_PRIOR, BL_FLAG_STRICT_MATH = 1, 2, 4, 8
+BL_FLAG_SITE_RE, BL_FLAG_OBS_RE = 16, 32
 
 
 class BiolithB200Error(RuntimeError):

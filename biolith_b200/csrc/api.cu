@@ -78,6 +78,10 @@ int occu_cs_chain_block_threads(int C);
 size_t occu_cs_chain_smem(const Layout& L, int nstage, int bt);
 cudaError_t launch_occu_cs_chain(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 
+int64_t occu_re_theta_dim(const Layout& L, int64_t S, uint32_t flags);
+int occu_re_n_small(const Layout& L, int64_t S, uint32_t flags);
+cudaError_t launch_occu_re(const EvalParams& p, int dtype, int64_t S, int grid_x, double sd_scale_site,
+                           double sd_scale_obs, cudaStream_t st);
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
 
@@ -279,8 +283,45 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
   return BL_OK;
 }
 
+// occu with random effects: own kernel (lane = site, elementwise gradient outputs), own workspace sizing
+static int eval_device_re(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st,
+                          double* logp64) {
+  if (ds->comm) return fail(BL_ERR_UNSUPPORTED, "random effects are not site-sharded");
+  const int64_t S = ds->desc.n_sites;
+  const int nqs = 1 + occu_re_n_small(ds->L, S, ds->desc.flags);
+  int grid_x = (int)std::min<int64_t>((S + kBlockThreads - 1) / kBlockThreads, (int64_t)ds->num_sms * 4);
+  if (grid_x < 1) grid_x = 1;
+  const size_t need = (size_t)grid_x * C * nqs;
+  if (need > ds->partial_cap || (size_t)C > ds->counters_cap) {
+    cudaDeviceSynchronize();
+    if (need > ds->partial_cap) {
+      cudaFree(ds->partial);
+      if (cudaMalloc(&ds->partial, need * sizeof(double)) != cudaSuccess) return fail(BL_ERR_NOMEM, "partials");
+      ds->partial_cap = need;
+    }
+    if ((size_t)C > ds->counters_cap) {
+      cudaFree(ds->counters);
+      const size_t n = (size_t)C + 16;
+      if (cudaMalloc(&ds->counters, n * sizeof(unsigned int)) != cudaSuccess) return fail(BL_ERR_NOMEM, "counters");
+      cudaMemset(ds->counters, 0, n * sizeof(unsigned int));
+      ds->counters_cap = n;
+    }
+  }
+  EvalParams p;
+  fill_params(ds, p);
+  p.theta = theta; p.logp = logp; p.logp64 = logp64; p.grad = grad;
+  p.partial = ds->partial; p.counters = ds->counters; p.C = C;
+  const double sc_s = ds->desc.prior_fp_a > 0 ? ds->desc.prior_fp_a : 1.0;
+  const double sc_o = ds->desc.prior_fp_b > 0 ? ds->desc.prior_fp_b : 1.0;
+  cudaError_t e = launch_occu_re(p, ds->desc.dtype, S, grid_x, sc_s, sc_o, st);
+  if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return BL_OK;
+}
+
 int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce,
                 double* logp64) {
+  if (ds->re) return eval_device_re(ds, theta, C, logp, grad, st, logp64);
   Plan* pl = nullptr;
   int rc = plan_for(ds, C, &pl);
   if (rc) return rc;
@@ -385,6 +426,9 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
     return fail(BL_ERR_INVALID, "occu_cs priors: Gamma(a, b) of sigma and the Normal scale of mu must be positive");
   if ((d->model == BL_MODEL_OCCU_RN || d->model == BL_MODEL_NMIXTURE) && (d->max_abundance < 1 || d->max_abundance > 1023))
     return fail(BL_ERR_INVALID, "max_abundance must be in [1, 1023]");
+  const bool re = (d->flags & (BL_FLAG_SITE_RE | BL_FLAG_OBS_RE)) != 0;
+  if (re && (d->model != BL_MODEL_OCCU || fpc || fpu))
+    return fail(BL_ERR_UNSUPPORTED, "random effects are accelerated for occu without false-positive extras only");
   if (d->n_sites > 0 && (!y || !X || !W)) return fail(BL_ERR_INVALID, "y/X/W is NULL");
   if ((d->flags & BL_FLAG_PRIOR) && (d->prior_beta_scale <= 0 || d->prior_alpha_scale <= 0))
     return fail(BL_ERR_INVALID, "prior scales must be positive");
@@ -402,6 +446,15 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
                 : d->model == BL_MODEL_OCCU_COP ? occu_cop_derived_slots(d->flags)
                 : d->model == BL_MODEL_OCCU_CS ? 4 : 0;
   ds->DS = ds->D + derived;
+  if (re) {
+    const int64_t Dre = occu_re_theta_dim(ds->L, d->n_sites, d->flags);
+    if (Dre > (int64_t)1 << 30) { delete ds; return fail(BL_ERR_UNSUPPORTED, "random-effect vector too long"); }
+    ds->re = true;
+    ds->force_engine = true;
+    ds->D = (int)Dre;
+    ds->DS = ds->D;
+    ds->n_extras = ((d->flags & BL_FLAG_SITE_RE) ? 1 : 0) + ((d->flags & BL_FLAG_OBS_RE) ? 1 : 0);
+  }
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, d->device);
   if (e != cudaSuccess) { delete ds; return fail(BL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
@@ -503,7 +556,7 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&ds->ev1);
     if (e2 != cudaSuccess) rc = fail(BL_ERR_CUDA, "stream/event create: %s", cudaGetErrorString(e2));
   }
-  if (rc == BL_OK && d->max_chains > 0) {
+  if (rc == BL_OK && d->max_chains > 0 && !ds->re) {
     Plan* pl = nullptr;
     rc = plan_for(ds, d->max_chains, &pl);
   }
@@ -612,6 +665,7 @@ int bl_eval_host(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp
 int bl_site_summary(bl_dataset* ds, const void* theta, int32_t n_draws, float* out) {
   if (!ds || !theta || !out) return fail(BL_ERR_INVALID, "NULL argument");
   if (n_draws < 1) return fail(BL_ERR_INVALID, "n_draws must be >= 1");
+  if (ds->re) return fail(BL_ERR_UNSUPPORTED, "per-unit summaries are not built for the random-effects likelihood");
   CU_TRY(cudaSetDevice(ds->desc.device));
   const size_t es = elem_size(ds->desc.dtype);
   const size_t U = (size_t)ds->L.n_units;

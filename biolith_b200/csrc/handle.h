@@ -44,6 +44,7 @@ struct bl_dataset {
   void* rn_scratch = nullptr;  // occu_rn global A_k scratch (only when it does not fit in smem)
   size_t rn_scratch_cap = 0;
   std::map<int, bl::Plan> plans;
+  bool re = false;            // occu with site / observation random effects (occu_re.cu): its own kernel and layout
   bool force_engine = false;  // BL_FLAG_STRICT_MATH: always use the site-parallel libm-accurate engine
   // bl_eval_host staging
   void *d_theta = nullptr, *d_out = nullptr, *h_theta = nullptr, *h_out = nullptr;

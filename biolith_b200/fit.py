@@ -101,7 +101,8 @@ def fit(
     _, _, obs_np4, _ = ensure_period_dim(None, None, _as_numpy(obs), None)
     n_sp = obs_np4.shape[0]
     n_periods = obs_np4.shape[2]
-    if n_sp > 1 and (fpc or fpu or name == "occu_cs"):
+    has_re = bool(prior_kw.get("site_random_effects") or prior_kw.get("obs_random_effects"))
+    if n_sp > 1 and (fpc or fpu or name == "occu_cs" or has_re):
         raise BiolithB200Error(-2, "fit", "n_species > 1 with shared false-positive / score parameters couples the "
                                "species and is outside the accelerated path")
     parts = []
@@ -175,11 +176,27 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abu
             grouped["prob_fp_constant"] = 1 / (1 + np.exp(-th[:, :, i])); i += 1
         if fpu:
             grouped["prob_fp_unoccupied"] = 1 / (1 + np.exp(-th[:, :, i])); i += 1
-    # small problems: also materialise the deterministic site the reference's tests read
     X = np.nan_to_num(np.asarray(_as_numpy(site_covs), dtype=np.float64))
     S = X.shape[0]
+    a_re = 0.0
+    if lk.site_random_effects or lk.obs_random_effects:
+        # theta = [beta | alpha | log sd_site | log sd_obs | a (S) | d (S) | o (S*P*J)]; numpyro's site layouts:
+        # site_re_* (S, Sp) inside plates site/species, obs_re (J, P, S, Sp) (occu.py:191-196, 215-218)
+        P_, J_ = lk.shape["n_periods"], lk.shape["n_replicates"]
+        if lk.site_random_effects:
+            grouped["site_re_sd"] = np.exp(th[:, :, i]); i += 1
+        if lk.obs_random_effects:
+            grouped["obs_re_sd"] = np.exp(th[:, :, i]); i += 1
+        if lk.site_random_effects:
+            a_re = th[:, :, i : i + S]
+            grouped["site_re_occ"] = a_re[..., None]; i += S
+            grouped["site_re_det"] = th[:, :, i : i + S][..., None]; i += S
+        if lk.obs_random_effects:
+            o = th[:, :, i : i + S * P_ * J_].reshape(th.shape[0], th.shape[1], S, P_, J_)
+            grouped["obs_re"] = o.transpose(0, 1, 4, 3, 2)[..., None]; i += S * P_ * J_
+    # small problems: also materialise the deterministic site the reference's tests read
     if S * num_chains * num_samples <= _MAX_DETERMINISTIC_ELEMS:
-        eta = th[:, :, 0:1] + np.einsum("cnk,sk->cns", th[:, :, 1 : Ks + 1], X)
+        eta = th[:, :, 0:1] + np.einsum("cnk,sk->cns", th[:, :, 1 : Ks + 1], X) + a_re
         det = np.exp(eta) if name in ("occu_rn", "nmixture") else 1 / (1 + np.exp(-eta))
         grouped["abundance" if name in ("occu_rn", "nmixture") else "psi"] = np.broadcast_to(
             det[:, :, None, :, None], det.shape[:2] + (n_periods, S, 1))  # (C,N,P,S,Sp)
@@ -190,8 +207,9 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abu
                 global_steps=res["global_steps"], wall_s=res["wall_s"], kernel_variant=lk.kernel_variant)
     # per-site posterior summaries (psi / occupancy probability / pointwise lppd, p_waic), streamed on the
     # GPU over <= 512 thinned draws: available at any n_sites, unlike the per-draw deterministic sites
-    flat = th.reshape(-1, th.shape[-1])
-    thin = flat[:: max(1, flat.shape[0] // 512)][:512]
-    info["site_summary"] = lk.site_summary(thin)
+    if not (lk.site_random_effects or lk.obs_random_effects):
+        flat = th.reshape(-1, th.shape[-1])
+        thin = flat[:: max(1, flat.shape[0] // 512)][:512]
+        info["site_summary"] = lk.site_summary(thin)
     lk.close()
     return grouped, extra, info

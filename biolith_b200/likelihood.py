@@ -66,6 +66,10 @@ class OccupancyLikelihood:
         prior_fp_rate: float = 1.0,
         prior_mu_scale: float = 10.0,
         prior_sigma: Tuple[float, float] = (5.0, 1.0),
+        site_random_effects: bool = False,
+        obs_random_effects: bool = False,
+        prior_site_re_sd_scale: float = 1.0,
+        prior_obs_re_sd_scale: float = 1.0,
         device: int = 0,
         max_chains: int = 0,
     ):
@@ -102,6 +106,12 @@ class OccupancyLikelihood:
             # occu_cs.py:29-30: Normal(0, s) on mu0 / mu1 and Gamma(a, b) on sigma0 / sigma1 travel in the
             # prior_fp_* slots of bl_desc (include/biolith_b200.h)
             prior_fp_beta, prior_fp_rate = tuple(prior_sigma), float(prior_mu_scale)
+        if site_random_effects or obs_random_effects:
+            # occu.py:170-173: HalfNormal(scale) on the two sd's travels in the (otherwise unused) prior_fp_a / _b slots
+            if model != "occu" or false_positives_constant or false_positives_unoccupied:
+                raise BiolithB200Error(-2, "unsupported", "random effects are accelerated for occu without "
+                                       "false-positive extras only")
+            prior_fp_beta = (float(prior_site_re_sd_scale), float(prior_obs_re_sd_scale))
         code, npdt = _DT[dtype]
         # the reference casts to the compute dtype on ingestion (jnp.array, data.py:135-140)
         data_dt = np.float64 if any(a.dtype == np.float64 for a in (site_covs, obs_covs, obs)) else np.float32
@@ -111,7 +121,8 @@ class OccupancyLikelihood:
         T = None if session_duration is None else np.ascontiguousarray(session_duration, dtype=data_dt)
         flags = (_lib.BL_FLAG_FP_CONSTANT if false_positives_constant else 0) | (
             _lib.BL_FLAG_FP_UNOCCUPIED if false_positives_unoccupied else 0) | (_lib.BL_FLAG_PRIOR if prior else 0) | (
-            _lib.BL_FLAG_STRICT_MATH if strict_math else 0)
+            _lib.BL_FLAG_STRICT_MATH if strict_math else 0) | (_lib.BL_FLAG_SITE_RE if site_random_effects else 0) | (
+            _lib.BL_FLAG_OBS_RE if obs_random_effects else 0)
         d = bl_desc(
             abi_version=_lib.BL_ABI_VERSION, model=_lib.BL_MODEL[model], dtype=code,
             data_dtype=_lib.BL_F64 if data_dt == np.float64 else _lib.BL_F32, flags=flags, device=device,
@@ -128,6 +139,7 @@ class OccupancyLikelihood:
         check(self._lib.bl_dataset_info(self._h, C.byref(info)), "bl_dataset_info")
         self.model, self.dtype, self.np_dtype, self.device = model, dtype, npdt, device
         self.shape = dict(n_sites=S, n_periods=P, n_replicates=J, n_site_covs=site_covs.shape[1], n_obs_covs=Ko)
+        self.site_random_effects, self.obs_random_effects = bool(site_random_effects), bool(obs_random_effects)
         self.theta_dim = info.theta_dim
         self.n_extras = info.n_extras
         self.packed_bytes = info.packed_bytes

@@ -73,14 +73,25 @@ def model_options(name, kwargs):
     def bad(msg, code=-2):
         return BiolithB200Error(code, "fit", msg)
 
+    re_kw = {}
     unknown = set(kwargs) - KEYWORDS[name]
     if unknown:
         raise bad(f"unknown keyword(s) for {name}: {sorted(unknown)} (accepted: {sorted(KEYWORDS[name])})", -1)
     if kwargs.get("coords") is not None:
         raise bad("coords (spatial HSGP effect) is outside the accelerated path (no fallback)")
-    for k in ("site_random_effects", "obs_random_effects"):
-        if kwargs.get(k):
-            raise bad(f"{k} is outside the accelerated path of fit() (no fallback)")
+    for k, pk, out in (("site_random_effects", "prior_site_re_sd", "prior_site_re_sd_scale"),
+                       ("obs_random_effects", "prior_obs_re_sd", "prior_obs_re_sd_scale")):
+        if not kwargs.get(k):
+            continue
+        if name != "occu" or kwargs.get("false_positives_constant") or kwargs.get("false_positives_unoccupied"):
+            raise bad(f"{k} is accelerated for occu without false-positive extras only (no fallback)")
+        re_kw[k] = True
+        pr = kwargs.get(pk)
+        if pr is not None:  # occu.py:38-39: HalfNormal(scale)
+            v = _dist_params(pr, "HalfNormal", ("scale",))
+            if v is None:
+                raise bad(f"{pk}: only HalfNormal(scale) priors are accelerated")
+            re_kw[out] = v[0]
     for k in ("regressor_occ", "regressor_det", "regressor_abu"):
         r = kwargs.get(k)
         if r is not None and getattr(r, "__name__", "") != "LinearRegression":
@@ -127,4 +138,5 @@ def model_options(name, kwargs):
             if v is None:
                 raise bad("prior_sigma: only a single Gamma(concentration, rate) prior is accelerated")
             prior_kw["prior_sigma"] = v
+    prior_kw.update(re_kw)
     return fpc, fpu, int(kwargs.get("max_abundance", 100)), prior_kw

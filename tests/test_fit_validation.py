@@ -12,8 +12,9 @@ def _data():
 
 
 @pytest.mark.parametrize("kw", [
-    dict(kernel="hmc"), dict(kernel="discrete_hmc_gibbs"), dict(site_random_effects=True),
-    dict(obs_random_effects=True), dict(coords=np.zeros((6, 2))), dict(init_strategy=lambda *a: None),
+    dict(kernel="hmc"), dict(kernel="discrete_hmc_gibbs"),
+    dict(site_random_effects=True, false_positives_constant=True),  # random effects: occu without fp extras only
+    dict(coords=np.zeros((6, 2))), dict(init_strategy=lambda *a: None),
     dict(init_strategy="median"),
 ])
 def test_options_outside_the_path_raise(kw):
@@ -21,6 +22,24 @@ def test_options_outside_the_path_raise(kw):
 
     with pytest.raises(bb.BiolithB200Error):
         bb.fit(bb.models.occu, **_data(), **kw)
+
+
+def test_random_effects_keywords():
+    from biolith_b200 import BiolithB200Error
+    from biolith_b200.models import model_options
+
+    class HalfNormal:
+        def __init__(self, scale):
+            self.scale = scale
+
+    _, _, _, kw = model_options("occu", dict(site_random_effects=True, prior_site_re_sd=HalfNormal(0.5)))
+    assert kw == {"site_random_effects": True, "prior_site_re_sd_scale": 0.5}
+    _, _, _, kw = model_options("occu", dict(obs_random_effects=True, site_random_effects=True))
+    assert kw == {"site_random_effects": True, "obs_random_effects": True}
+    for model, k in (("occu_rn", dict(site_random_effects=True)), ("occu_cop", dict(obs_random_effects=True)),
+                     ("occu", dict(site_random_effects=True, prior_site_re_sd=object()))):
+        with pytest.raises(BiolithB200Error):
+            model_options(model, k)
 
 
 def test_unknown_model_and_regressor_raise():
