@@ -592,6 +592,39 @@ def run_site_sharded(args, dist, rank, world, device):
             dist.barrier()
         out[label] = entry
         del X, W, y
+    if world >= 4 and world % 2 == 0:
+        # hybrid chains x sites grid (third row): site groups of 2 ranks share 256 chains and exchange
+        # inside the group only; the world / 2 groups run different chains and never talk
+        model, kw, _, _ = WORKLOADS["occu_sites16m_c256"]
+        WORKLOADS["_site_tmp"] = (model, {**kw, "n_sites": 2_000_000}, chains, "sites")
+        g, site_rank, _ = sharded.hybrid_layout(rank, world, 2)
+        _, X, W, y, _, _ = make_data("_site_tmp", site_rank)
+        th_g = np.random.default_rng(500 + g).uniform(-2, 2, size=(chains, 10)).astype(np.float32)
+        entry = {"site_group_size": 2, "chain_groups": world // 2, "sites_per_rank": 2_000_000,
+                 "chains_total": chains * (world // 2)}
+        with bb.OccupancyLikelihood(model, X, W, y, None, device=device, max_chains=chains) as lk:
+            _, _, sub = sharded.attach_hybrid(lk, dist, rank, world, 2, chains, mode="p2p")
+            dist.barrier()
+            ms = tmax(_time_eval(lib, lk, th_g, device, steps=args.steps))
+            lp, gr = lk.logp_and_grad(th_g)
+            k = 4
+            th64 = th_g[:k].astype(np.float64)
+            olp, ogr = c_oracle.occu_logp_grad(th64, X, W, y, dtype=np.float64, prior=False,
+                                               nthreads=max(1, host_threads() // world))
+            t = torch.tensor(np.concatenate([olp[:, None], ogr], axis=1), dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, group=sub._group)
+            ref = t.cpu().numpy()
+            ref[:, 0] += (-0.5 * th64 ** 2 - 0.9189385332046727).sum(axis=1)
+            ref[:, 1:] -= th64
+            got = np.concatenate([lp.astype(np.float64)[:k, None], gr.astype(np.float64)[:k]], axis=1)
+            err = np.abs(got - ref) / np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
+            worst = torch.tensor([float(err.max())], dtype=torch.float64, device="cuda")
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            entry.update({"ms_per_eval": ms, "chain_evals_per_s": entry["chains_total"] / (ms * 1e-3),
+                          "max_rel_err_vs_fp64_c_oracle_all_groups": float(worst[0]), "exchange": "p2p"})
+            lib.bl_dataset_detach_comm(lk.handle)
+        dist.barrier()
+        out[f"hybrid_{world // 2}_chain_groups_x_2_site_shards"] = entry
     WORKLOADS.pop("_site_tmp", None)
     out["note"] = ("exchange = [C, 1+D] fp64 sums (22 KB): 'p2p' is ONE fused kernel over CUDA-IPC peer memory "
                    "(publish, flag, rank-ordered sum, priors), 'nccl' is ncclAllReduce + finalize; oracle check = fp64 "

@@ -5,6 +5,10 @@
 * site sharding: ``shard_range`` gives each rank a contiguous block of sites; ``attach_site_sharding``
   wires the handle so that every evaluation sums the ranks' fp64 partial sums either with one
   ``ncclAllReduce`` (mode "nccl") or with the fused CUDA-IPC peer-memory kernel (mode "p2p").
+* hybrid chains x sites grid (third row): ``hybrid_layout`` cuts the world into site groups of
+  ``site_group_size`` consecutive ranks; the ranks of a group hold the site shards of ONE dataset and share the
+  same chains (exchange inside the group only), different groups run different chains and never talk.
+  ``attach_hybrid`` builds the per-group sub-communicator and attaches it.
 
 ``dist`` is an initialised ``torch.distributed`` module (or any object with the same
 ``broadcast_object_list`` / ``all_gather_object`` / ``gather_object`` functions): torch is only the
@@ -75,6 +79,51 @@ def attach_site_sharding(lk, dist, rank: int, world: int, max_chains: int, mode:
     else:
         raise ValueError("mode must be 'nccl' or 'p2p'")
     return mode
+
+
+class _SubGroup:
+    """The slice of a ``torch.distributed``-like module that ``attach_site_sharding`` needs, restricted to one
+    process group whose members are the global ranks ``members`` (group rank = position in that list)."""
+
+    def __init__(self, dist, group, members):
+        self._dist, self._group, self._members = dist, group, list(members)
+
+    def broadcast_object_list(self, box, src=0):
+        self._dist.broadcast_object_list(box, src=self._members[src], group=self._group)
+
+    def all_gather_object(self, out, obj):
+        self._dist.all_gather_object(out, obj, group=self._group)
+
+    def barrier(self):
+        self._dist.barrier(group=self._group)
+
+
+def hybrid_layout(rank: int, world: int, site_group_size: int):
+    """-> (chain_group, site_rank, members): ``world`` = n_chain_groups x site_group_size; ranks
+    [g * size, (g + 1) * size) form site group g (consecutive ranks = neighbouring GPUs)."""
+    if site_group_size < 1 or world % site_group_size != 0:
+        raise ValueError("world must be a multiple of site_group_size")
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    g = rank // site_group_size
+    return g, rank % site_group_size, list(range(g * site_group_size, (g + 1) * site_group_size))
+
+
+def attach_hybrid(lk, dist, rank: int, world: int, site_group_size: int, max_chains: int, mode: str = "nccl"):
+    """Chains x sites grid: after this call ``lk`` (holding site shard ``site_rank`` of its group's dataset)
+    evaluates the log-density of the whole group's sites; groups are independent (their own chains, no traffic
+    between them).  Every rank must call it (``new_group`` is collective over the world).  Returns
+    ``(chain_group, site_rank, subgroup)``."""
+    groups = []
+    n_groups = world // site_group_size
+    for g in range(n_groups):  # every rank creates every group, in the same order (torch.distributed contract)
+        members = list(range(g * site_group_size, (g + 1) * site_group_size))
+        groups.append((dist.new_group(ranks=members), members))
+    g, site_rank, members = hybrid_layout(rank, world, site_group_size)
+    sub = _SubGroup(dist, groups[g][0], members)
+    if site_group_size > 1:
+        attach_site_sharding(lk, sub, site_rank, site_group_size, max_chains, mode=mode)
+    return g, site_rank, sub
 
 
 def comm_error(lk) -> int:

@@ -69,3 +69,62 @@ def test_gloo_world2_exchange_and_gather():
     assert res[0][2] == [0, 1] and res[1][2] == [0, 1]
     assert res[0][3] == (6, 5, 2) and res[0][4] == [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
     assert res[1][3] is None
+
+
+def test_hybrid_layout_is_a_grid():
+    from biolith_b200.sharded import hybrid_layout
+
+    seen = {}
+    for r in range(8):
+        g, sr, members = hybrid_layout(r, 8, 2)
+        assert members == [2 * g, 2 * g + 1] and members[sr] == r
+        seen.setdefault(g, []).append(sr)
+    assert seen == {0: [0, 1], 1: [0, 1], 2: [0, 1], 3: [0, 1]}
+    assert hybrid_layout(5, 8, 8)[:2] == (0, 5) and hybrid_layout(5, 8, 1)[:2] == (5, 0)
+    with pytest.raises(ValueError):
+        hybrid_layout(0, 6, 4)
+
+
+def _hybrid_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from biolith_b200 import sharded
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # the sub-communicator plumbing of attach_hybrid without a GPU handle: the NCCL-id / IPC-handle exchange
+        # pattern runs inside each site group only
+        groups = [(dist.new_group(ranks=[2 * g, 2 * g + 1]), [2 * g, 2 * g + 1]) for g in range(world // 2)]
+        g, site_rank, members = sharded.hybrid_layout(rank, world, 2)
+        sub = sharded._SubGroup(dist, groups[g][0], members)
+        uid = sharded.exchange_unique_id(sub, site_rank, lambda: bytes([g]) * 128)
+        handles = [None] * 2
+        sub.all_gather_object(handles, bytes([rank]) * sharded.IPC_HANDLE_BYTES)
+        sub.barrier()
+        q.put((rank, g, site_rank, uid[0], [h[0] for h in handles]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world4_hybrid_subgroups():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # every rank got ITS group's id (made by the group's rank 0) and only its group's handles
+    assert [(r[1], r[2], r[3], r[4]) for r in res] == [(0, 0, 0, [0, 1]), (0, 1, 0, [0, 1]), (1, 0, 1, [2, 3]),
+                                                       (1, 1, 1, [2, 3])]
