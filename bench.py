@@ -215,6 +215,8 @@ def main():
     ap.add_argument("--no-nuts", action="store_true", help="skip the NUTS ESS/s section")
     ap.add_argument("--no-other-workloads", action="store_true", help="skip the configs[2]/[3] lines (N=1)")
     ap.add_argument("--no-site-sharded", action="store_true", help="skip the configs[4] block (N>1)")
+    ap.add_argument("--site-sharded-timeout", type=float, default=300.0,
+                    help="watchdog of the configs[4] block: the headline line is printed regardless")
     ap.add_argument("--strict-math", action="store_true", help="BL_FLAG_STRICT_MATH (libm expf/log1pf)")
     ap.add_argument("--theta", default="uniform", choices=["uniform", "mode"],
                     help="chain positions: U(-2,2) (init_to_uniform, default) or within 0.01 of the simulating truth "
@@ -353,12 +355,7 @@ def main():
     nuts = None
     if not args.no_nuts:
         nuts = run_nuts(args, lk, chains, rank, world, shard, dist)
-    site_sharded = None
-    if world > 1 and shard == "chains" and args.workload == "occu_1m_x8_c1024" and not args.no_site_sharded:
-        # the one multi-GPU mode with a data-path collective (BASELINE configs[4]); measured in the same run so
-        # that the driver's SCALE record carries it
-        site_sharded = run_site_sharded(args, dist, rank, world, local_rank)
-
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         ms_launch = total_ms / args.steps
@@ -380,8 +377,6 @@ def main():
             line["exchange_check"] = exchange_check
         if nuts is not None:
             line["nuts"] = nuts
-        if site_sharded is not None:
-            line["site_sharded"] = site_sharded
         if world == 1 and args.workload == "occu_1m_x8_c1024" and not args.no_other_workloads:
             line["other_workloads"] = other_workloads(lib, local_rank, args)
         if world == 1 and model == "occu" and args.dtype == "float32" and not args.strict_math:
@@ -399,8 +394,29 @@ def main():
                 line["strict_math"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline and world == 1 and model in ("occu", "occu_cop", "occu_rn"):
             line["cpu_baseline"] = cpu_baseline(X, W, y, D, args.cpu_chains, model, make_data.session_duration)
-        print(json.dumps(_finite(line)), flush=True)
     lk.close()
+    if world > 1 and shard == "chains" and args.workload == "occu_1m_x8_c1024" and not args.no_site_sharded:
+        # the one multi-GPU mode with a data-path collective (BASELINE configs[4]); measured in the same run so that
+        # the driver's SCALE record carries it -- LAST and under a watchdog: whatever happens in here (a peer that
+        # never arrives in a collective), rank 0 still prints the line it has already measured and every rank exits
+        def give_up():
+            if rank == 0:
+                line["site_sharded"] = {"error": f"no result within {args.site_sharded_timeout} s (watchdog)"}
+                print(json.dumps(_finite(line)), flush=True)
+            os._exit(0)
+
+        dog = threading.Timer(args.site_sharded_timeout, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            site_sharded = run_site_sharded(args, dist, rank, world, local_rank)
+        except Exception as exc:  # noqa: BLE001 - never fatal for the headline line
+            site_sharded = {"error": str(exc)[:300]}
+        dog.cancel()
+        if rank == 0:
+            line["site_sharded"] = site_sharded
+    if rank == 0:
+        print(json.dumps(_finite(line)), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -536,6 +552,12 @@ def run_site_sharded(args, dist, rank, world, device):
     lib = bb._lib.load()
     chains = 256
     out = {"chains": chains, "world": world}
+    t_start = time.perf_counter()
+
+    def stage(msg):  # progress on stderr: a watchdog exit then shows how far the block got
+        if rank == 0:
+            print(f"[site_sharded +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     sizes = {"weak_2m_sites_per_rank": 2_000_000}
     if 16_000_000 // world != 2_000_000:
         sizes[f"strong_16m_sites_over_{world}_ranks"] = 16_000_000 // world
@@ -549,13 +571,16 @@ def run_site_sharded(args, dist, rank, world, device):
     for label, n_sites in sizes.items():
         model, kw, _, _ = WORKLOADS["occu_sites16m_c256"]
         WORKLOADS["_site_tmp"] = (model, {**kw, "n_sites": n_sites}, chains, "sites")
+        stage(f"{label}: generating {n_sites} sites per rank")
         _, X, W, y, _, _ = make_data("_site_tmp", rank)
         entry = {"sites_per_rank": n_sites, "sites_total": n_sites * world}
+        stage(f"{label}: local-only timing")
         with bb.OccupancyLikelihood(model, X, W, y, None, device=device, max_chains=chains) as plain:
             dist.barrier()
             entry["ms_per_eval_local_only"] = tmax(_time_eval(lib, plain, theta, device, steps=args.steps))
         ref = None
         for mode in ("p2p", "nccl"):
+            stage(f"{label}: exchange mode {mode}")
             with bb.OccupancyLikelihood(model, X, W, y, None, device=device, max_chains=chains) as lk:
                 sharded.attach_site_sharding(lk, dist, rank, world, chains, mode=mode)
                 dist.barrier()
@@ -598,7 +623,9 @@ def run_site_sharded(args, dist, rank, world, device):
         model, kw, _, _ = WORKLOADS["occu_sites16m_c256"]
         WORKLOADS["_site_tmp"] = (model, {**kw, "n_sites": 2_000_000}, chains, "sites")
         g, site_rank, _ = sharded.hybrid_layout(rank, world, 2)
+        stage("hybrid: generating data")
         _, X, W, y, _, _ = make_data("_site_tmp", site_rank)
+        stage("hybrid: attach + timing")
         th_g = np.random.default_rng(500 + g).uniform(-2, 2, size=(chains, 10)).astype(np.float32)
         entry = {"site_group_size": 2, "chain_groups": world // 2, "sites_per_rank": 2_000_000,
                  "chains_total": chains * (world // 2)}

@@ -74,6 +74,7 @@ SIGNATURES = {
     "bl_eval_host": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "bl_eval_timed": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.POINTER(C.c_float)]),
     "bl_site_summary": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "bl_obs_loglik": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "bl_nuts_create": (C.c_int, [_P, C.POINTER(bl_nuts_config), _P, C.POINTER(_P)]),
     "bl_nuts_run": (C.c_int, [_P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bl_nuts_get": (C.c_int, [_P] * 11),

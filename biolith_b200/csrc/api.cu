@@ -82,6 +82,9 @@ int64_t occu_re_theta_dim(const Layout& L, int64_t S, uint32_t flags);
 int occu_re_n_small(const Layout& L, int64_t S, uint32_t flags);
 cudaError_t launch_occu_re(const EvalParams& p, int dtype, int64_t S, int grid_x, double sd_scale_site,
                            double sd_scale_obs, cudaStream_t st);
+cudaError_t launch_obs_loglik(const EvalParams& p, int dtype, int n_draws, float* lppd, float* var, cudaStream_t st);
+int eval_device_multi(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st,
+                      double* logp64, void (*fill)(const bl_dataset*, EvalParams&));
 int comm_post_eval(bl_dataset* ds, EvalParams& p, cudaStream_t st);
 void comm_destroy(bl_dataset* ds);
 
@@ -321,6 +324,7 @@ static int eval_device_re(bl_dataset* ds, const void* theta, int C, void* logp, 
 
 int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad, cudaStream_t st, int allreduce,
                 double* logp64) {
+  if (!ds->species.empty()) return eval_device_multi(ds, theta, C, logp, grad, st, logp64, fill_params);
   if (ds->re) return eval_device_re(ds, theta, C, logp, grad, st, logp64);
   Plan* pl = nullptr;
   int rc = plan_for(ds, C, &pl);
@@ -412,7 +416,43 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   if (d->n_sites < 0 || d->n_periods < 1 || d->n_replicates < 1 || d->n_site_covs < 0 || d->n_obs_covs < 0)
     return fail(BL_ERR_INVALID, "bad shape S=%lld P=%d J=%d Ks=%d Ko=%d", (long long)d->n_sites, d->n_periods,
                 d->n_replicates, d->n_site_covs, d->n_obs_covs);
-  if (d->n_species != 1) return fail(BL_ERR_UNSUPPORTED, "n_species=%d: one handle per species", d->n_species);
+  if (d->n_species < 1) return fail(BL_ERR_INVALID, "n_species must be >= 1");
+  if (d->n_species > 1) {
+    // the species plate (occu.py:182-186): one likelihood-only child per species, extras shared (multi.cu)
+    if (d->flags & (BL_FLAG_SITE_RE | BL_FLAG_OBS_RE))
+      return fail(BL_ERR_UNSUPPORTED, "random effects with n_species > 1 are outside the accelerated path");
+    bl_dataset* parent = new (std::nothrow) bl_dataset();
+    if (!parent) return fail(BL_ERR_NOMEM, "host allocation failed");
+    parent->desc = *d;
+    const size_t ds_in = elem_size(d->data_dtype);
+    const size_t stride = (size_t)d->n_sites * d->n_periods * d->n_replicates * ds_in;
+    int rc = BL_OK;
+    for (int sp = 0; sp < d->n_species && rc == BL_OK; ++sp) {
+      bl_desc dc = *d;
+      dc.n_species = 1;
+      dc.flags &= ~BL_FLAG_PRIOR;
+      bl_dataset* child = nullptr;
+      rc = bl_dataset_create(&dc, (const char*)y + sp * stride, X, W, T, &child);
+      if (rc == BL_OK) parent->species.push_back(child);
+    }
+    if (rc == BL_OK) {
+      bl_dataset* c0 = parent->species[0];
+      parent->L = c0->L;
+      parent->n_extras = c0->n_extras;
+      parent->D = d->n_species * (c0->L.ks + 1 + c0->L.ko + 1) + c0->n_extras;
+      parent->DS = parent->D;
+      parent->num_sms = c0->num_sms;
+      parent->smem_limit = c0->smem_limit;
+      for (bl_dataset* c : parent->species) { parent->n_masked += c->n_masked; parent->packed_bytes += c->packed_bytes; }
+      cudaError_t e2 = cudaStreamCreateWithFlags(&parent->own_stream, cudaStreamNonBlocking);
+      if (e2 == cudaSuccess) e2 = cudaEventCreate(&parent->ev0);
+      if (e2 == cudaSuccess) e2 = cudaEventCreate(&parent->ev1);
+      if (e2 != cudaSuccess) rc = fail(BL_ERR_CUDA, "stream/event create: %s", cudaGetErrorString(e2));
+    }
+    if (rc != BL_OK) { bl_dataset_destroy(parent); return rc; }
+    *out = parent;
+    return BL_OK;
+  }
   if (d->n_site_covs > kMaxCov || d->n_obs_covs > kMaxCov)
     return fail(BL_ERR_UNSUPPORTED, "more than %d covariates per predictor", kMaxCov);
   const bool fpc = d->flags & BL_FLAG_FP_CONSTANT, fpu = d->flags & BL_FLAG_FP_UNOCCUPIED;
@@ -568,6 +608,9 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
 int bl_dataset_destroy(bl_dataset* ds) {
   if (!ds) return BL_OK;
   cudaSetDevice(ds->desc.device);
+  for (bl_dataset* c : ds->species) bl_dataset_destroy(c);
+  ds->species.clear();
+  cudaFree(ds->ms_theta); cudaFree(ds->ms_lp); cudaFree(ds->ms_lp64); cudaFree(ds->ms_grad);
   comm_destroy(ds);
   cudaFree(ds->packed); cudaFree(ds->packed_signed); cudaFree(ds->packed_rn2); cudaFree(ds->partial); cudaFree(ds->counters); cudaFree(ds->sums);
   cudaFree(ds->rn_scratch);
@@ -604,6 +647,13 @@ int bl_dataset_export_mask(const bl_dataset* ds, uint8_t* mask_out) {
   if (!ds || !mask_out) return fail(BL_ERR_INVALID, "NULL argument");
   const size_t n = (size_t)ds->L.n_units * ds->L.J;
   if (n == 0) return BL_OK;
+  if (!ds->species.empty()) {  // n_species > 1: (Sp, S, P, J), species-major like obs
+    for (size_t sp = 0; sp < ds->species.size(); ++sp) {
+      const int rc = bl_dataset_export_mask(ds->species[sp], mask_out + sp * n);
+      if (rc) return rc;
+    }
+    return BL_OK;
+  }
   CU_TRY(cudaSetDevice(ds->desc.device));
   uint8_t* d_mask = nullptr;
   CU_TRY(cudaMalloc(&d_mask, n));
@@ -662,10 +712,45 @@ int bl_eval_host(bl_dataset* ds, const void* theta, int32_t n_chains, void* logp
   return BL_OK;
 }
 
+int bl_obs_loglik(bl_dataset* ds, const void* theta, int32_t n_draws, float* lppd_out, float* var_out) {
+  if (!ds || !theta || !lppd_out) return fail(BL_ERR_INVALID, "NULL argument");
+  if (n_draws < 1) return fail(BL_ERR_INVALID, "n_draws must be >= 1");
+  if (ds->desc.model != BL_MODEL_OCCU || ds->re || !ds->species.empty() ||
+      (ds->desc.flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)))
+    return fail(BL_ERR_UNSUPPORTED, "per-observation log-likelihood: occu without false-positive / random-effect extras");
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  const size_t es = elem_size(ds->desc.dtype);
+  const size_t nobs = (size_t)ds->L.n_units * ds->L.J;
+  if (nobs == 0) return BL_OK;
+  void* d_theta = nullptr;
+  float *d_l = nullptr, *d_v = nullptr;
+  int rc = BL_OK;
+  cudaError_t e = cudaSuccess;
+  do {
+#define CU_BRK(expr) if ((e = (expr)) != cudaSuccess) { rc = fail(BL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e)); break; }
+    CU_BRK(cudaMalloc(&d_theta, (size_t)n_draws * ds->D * es));
+    CU_BRK(cudaMalloc(&d_l, nobs * sizeof(float)));
+    if (var_out) CU_BRK(cudaMalloc(&d_v, nobs * sizeof(float)));
+    CU_BRK(cudaMemcpy(d_theta, theta, (size_t)n_draws * ds->D * es, cudaMemcpyHostToDevice));
+    EvalParams p;
+    fill_params(ds, p);
+    p.theta = d_theta;
+    CU_BRK(launch_obs_loglik(p, ds->desc.dtype, n_draws, d_l, d_v, ds->own_stream));
+    g_launches.fetch_add(1);
+    CU_BRK(cudaStreamSynchronize(ds->own_stream));
+    CU_BRK(cudaMemcpy(lppd_out, d_l, nobs * sizeof(float), cudaMemcpyDeviceToHost));
+    if (var_out) CU_BRK(cudaMemcpy(var_out, d_v, nobs * sizeof(float), cudaMemcpyDeviceToHost));
+#undef CU_BRK
+  } while (0);
+  cudaFree(d_theta); cudaFree(d_l); cudaFree(d_v);
+  return rc;
+}
+
 int bl_site_summary(bl_dataset* ds, const void* theta, int32_t n_draws, float* out) {
   if (!ds || !theta || !out) return fail(BL_ERR_INVALID, "NULL argument");
   if (n_draws < 1) return fail(BL_ERR_INVALID, "n_draws must be >= 1");
   if (ds->re) return fail(BL_ERR_UNSUPPORTED, "per-unit summaries are not built for the random-effects likelihood");
+  if (!ds->species.empty()) return fail(BL_ERR_UNSUPPORTED, "per-unit summaries: use one handle per species");
   CU_TRY(cudaSetDevice(ds->desc.device));
   const size_t es = elem_size(ds->desc.dtype);
   const size_t U = (size_t)ds->L.n_units;

@@ -2,6 +2,7 @@
 #pragma once
 #include <atomic>
 #include <map>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -44,6 +45,11 @@ struct bl_dataset {
   void* rn_scratch = nullptr;  // occu_rn global A_k scratch (only when it does not fit in smem)
   size_t rn_scratch_cap = 0;
   std::map<int, bl::Plan> plans;
+  // n_species > 1 (multi.cu): one likelihood-only child handle per species + the gather / combine workspace
+  std::vector<bl_dataset*> species;
+  void *ms_theta = nullptr, *ms_lp = nullptr, *ms_grad = nullptr;
+  double* ms_lp64 = nullptr;
+  int ms_cap = 0;
   bool re = false;            // occu with site / observation random effects (occu_re.cu): its own kernel and layout
   bool force_engine = false;  // BL_FLAG_STRICT_MATH: always use the site-parallel libm-accurate engine
   // bl_eval_host staging

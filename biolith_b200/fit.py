@@ -102,11 +102,17 @@ def fit(
     n_sp = obs_np4.shape[0]
     n_periods = obs_np4.shape[2]
     has_re = bool(prior_kw.get("site_random_effects") or prior_kw.get("obs_random_effects"))
-    if n_sp > 1 and (fpc or fpu or name == "occu_cs" or has_re):
-        raise BiolithB200Error(-2, "fit", "n_species > 1 with shared false-positive / score parameters couples the "
-                               "species and is outside the accelerated path")
+    if n_sp > 1 and has_re:
+        raise BiolithB200Error(-2, "fit", "random effects with n_species > 1 are outside the accelerated path")
     parts = []
-    for sp in range(n_sp):
+    if n_sp > 1 and (fpc or fpu or name == "occu_cs"):
+        # the false-positive / score parameters are sampled once, outside the species plate (occu.py:146-157,
+        # occu_cs.py:146-154): they couple the species -> ONE composite handle, one joint NUTS run (csrc/multi.cu)
+        parts.append(_fit_one(name, site_covs, obs_covs, obs_np4, session_duration, fpc, fpu, max_abundance,
+                              dtype, device, num_chains, num_warmup, num_samples, random_seed, max_tree_depth,
+                              target_accept_prob, timeout, prior_kw, n_periods, init_strategy))
+        n_sp = 1  # the single part already carries every species
+    for sp in range(n_sp if not parts else 0):
         # species are independent problems sharing the covariates (one handle each, occu.py:182-186)
         parts.append(_fit_one(name, site_covs, obs_covs, obs_np4[sp:sp + 1], session_duration, fpc, fpu, max_abundance,
                               dtype, device, num_chains, num_warmup, num_samples, random_seed + 7919 * sp,
@@ -156,11 +162,13 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abu
 
     th = res["samples"].astype(np.float64)  # (C, N, D)
     Ks, Ko = lk.shape["n_site_covs"], lk.shape["n_obs_covs"]
+    Sp = lk.n_species  # theta = [beta (Sp x Kb) | alpha (Sp x Ka) | extras]; Sp = 1 unless the species are coupled
+    nb, na = Sp * (Ks + 1), Sp * (Ko + 1)
     grouped = {
-        "beta": th[:, :, None, : Ks + 1],  # (C, N, n_species, Kb) like numpyro's plate layout
-        "alpha": th[:, :, None, Ks + 1 : Ks + Ko + 2],
+        "beta": th[:, :, :nb].reshape(th.shape[0], th.shape[1], Sp, Ks + 1),  # (C, N, n_species, Kb): numpyro's layout
+        "alpha": th[:, :, nb : nb + na].reshape(th.shape[0], th.shape[1], Sp, Ko + 1),
     }
-    i = Ks + Ko + 2
+    i = nb + na
     if name == "occu_cs":  # occu_cs.py:148-154; mu1 = mu0 + exp(x) (left-truncated at mu0)
         grouped["mu0"] = th[:, :, i]
         grouped["mu1"] = th[:, :, i] + np.exp(th[:, :, i + 1])
@@ -196,10 +204,13 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abu
             grouped["obs_re"] = o.transpose(0, 1, 4, 3, 2)[..., None]; i += S * P_ * J_
     # small problems: also materialise the deterministic site the reference's tests read
     if S * num_chains * num_samples <= _MAX_DETERMINISTIC_ELEMS:
-        eta = th[:, :, 0:1] + np.einsum("cnk,sk->cns", th[:, :, 1 : Ks + 1], X) + a_re
+        b = grouped["beta"]  # (C, N, Sp, Kb)
+        eta = b[..., 0][:, :, None, :] + np.einsum("cnpk,sk->cnsp", b[..., 1:], X)  # (C, N, S, Sp)
+        if not np.isscalar(a_re):
+            eta = eta + a_re[..., None]
         det = np.exp(eta) if name in ("occu_rn", "nmixture") else 1 / (1 + np.exp(-eta))
         grouped["abundance" if name in ("occu_rn", "nmixture") else "psi"] = np.broadcast_to(
-            det[:, :, None, :, None], det.shape[:2] + (n_periods, S, 1))  # (C,N,P,S,Sp)
+            det[:, :, None, :, :], det.shape[:2] + (n_periods, S, Sp))  # (C,N,P,S,Sp)
     extra = dict(diverging=res["diverging"], accept_prob=res["accept_prob"], num_steps=res["num_steps"],
                  potential_energy=res["potential_energy"])
     info = dict(step_size=res["step_size"], inverse_mass_matrix=res["inverse_mass_matrix"],
@@ -207,7 +218,7 @@ def _fit_one(name, site_covs, obs_covs, obs, session_duration, fpc, fpu, max_abu
                 global_steps=res["global_steps"], wall_s=res["wall_s"], kernel_variant=lk.kernel_variant)
     # per-site posterior summaries (psi / occupancy probability / pointwise lppd, p_waic), streamed on the
     # GPU over <= 512 thinned draws: available at any n_sites, unlike the per-draw deterministic sites
-    if not (lk.site_random_effects or lk.obs_random_effects):
+    if not (lk.site_random_effects or lk.obs_random_effects or Sp > 1):
         flat = th.reshape(-1, th.shape[-1])
         thin = flat[:: max(1, flat.shape[0] // 512)][:512]
         info["site_summary"] = lk.site_summary(thin)

@@ -96,8 +96,9 @@ class OccupancyLikelihood:
             raise ValueError("site_covs and obs_covs must have the same number of sites")
         if obs.shape[1:] != (S, P, J):
             raise ValueError("obs must have shape (n_species, n_sites, n_periods, n_replicates)")
-        if obs.shape[0] != 1:
-            raise BiolithB200Error(-2, "unsupported", "n_species > 1: create one handle per species")
+        n_species = obs.shape[0]
+        if n_species > 1 and (site_random_effects or obs_random_effects):
+            raise BiolithB200Error(-2, "unsupported", "random effects with n_species > 1 are outside the accelerated path")
         if session_duration is not None and model != "occu_cop":
             session_duration = None
         if session_duration is not None and session_duration.shape != (S, P, J):
@@ -126,7 +127,7 @@ class OccupancyLikelihood:
         d = bl_desc(
             abi_version=_lib.BL_ABI_VERSION, model=_lib.BL_MODEL[model], dtype=code,
             data_dtype=_lib.BL_F64 if data_dt == np.float64 else _lib.BL_F32, flags=flags, device=device,
-            n_sites=S, n_periods=P, n_replicates=J, n_site_covs=site_covs.shape[1], n_obs_covs=Ko, n_species=1,
+            n_sites=S, n_periods=P, n_replicates=J, n_site_covs=site_covs.shape[1], n_obs_covs=Ko, n_species=n_species,
             max_abundance=int(max_abundance), max_chains=int(max_chains), reserved0=0,
             prior_beta_loc=prior_beta[0], prior_beta_scale=prior_beta[1],
             prior_alpha_loc=prior_alpha[0], prior_alpha_scale=prior_alpha[1],
@@ -139,6 +140,7 @@ class OccupancyLikelihood:
         check(self._lib.bl_dataset_info(self._h, C.byref(info)), "bl_dataset_info")
         self.model, self.dtype, self.np_dtype, self.device = model, dtype, npdt, device
         self.shape = dict(n_sites=S, n_periods=P, n_replicates=J, n_site_covs=site_covs.shape[1], n_obs_covs=Ko)
+        self.n_species = n_species
         self.site_random_effects, self.obs_random_effects = bool(site_random_effects), bool(obs_random_effects)
         self.theta_dim = info.theta_dim
         self.n_extras = info.n_extras
@@ -222,10 +224,28 @@ class OccupancyLikelihood:
             "waic": float(-2.0 * (lppd.sum() - p_waic.sum())),
         }
 
+    def pointwise_loglik(self, theta_draws) -> dict:
+        """Per-observation lppd / p_waic over a batch of draws with the definitions of the reference's
+        ``lppd`` / ``waic`` (biolith/evaluation/lppd.py:51-61, waic.py:60-82), z integrated out per draw as in its
+        closed form ``log_likelihood_manual`` (evaluation/log_likelihood.py:55-98).  Streamed on the GPU: arrays are
+        (n_sites, n_periods, n_replicates), NaN where the observation is masked; totals run over valid observations."""
+        th = np.ascontiguousarray(theta_draws, dtype=self.np_dtype)
+        if th.ndim != 2 or th.shape[1] != self.theta_dim:
+            raise ValueError(f"theta_draws must have shape (N, {self.theta_dim})")
+        s = self.shape
+        shp = (s["n_sites"], s["n_periods"], s["n_replicates"])
+        lppd = np.empty(shp, dtype=np.float32)
+        var = np.empty(shp, dtype=np.float32)
+        check(self._lib.bl_obs_loglik(self._h, th.ctypes.data, th.shape[0], lppd.ctypes.data, var.ctypes.data),
+              "bl_obs_loglik")
+        tot, pw = float(np.nansum(lppd.astype(np.float64))), float(np.nansum(var.astype(np.float64)))
+        return {"lppd": lppd, "p_waic": var, "lppd_total": tot, "p_waic_total": pw, "waic": -2.0 * (tot - pw)}
+
     def mask(self) -> np.ndarray:
         """(S, P, J) bool: which observations enter the likelihood (the bit-exact mask contract)."""
         s = self.shape
-        out = np.empty((s["n_sites"], s["n_periods"], s["n_replicates"]), dtype=np.uint8)
+        shp = (s["n_sites"], s["n_periods"], s["n_replicates"])
+        out = np.empty(shp if self.n_species == 1 else (self.n_species,) + shp, dtype=np.uint8)
         check(self._lib.bl_dataset_export_mask(self._h, out.ctypes.data), "bl_dataset_export_mask")
         return out.astype(bool)
 

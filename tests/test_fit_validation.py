@@ -87,9 +87,6 @@ def test_occu_cs_prior_surface():
                dict(prior_sigma=Normal(0, 1)), dict(prior_sigma=(Gamma(5, 1), Gamma(5, 1)))):
         with pytest.raises(bb.BiolithB200Error):
             bb.fit(bb.models.occu_cs, **d, **kw)
-    d2 = dict(d, obs=rng.normal(size=(2, 6, 1, 3)))  # shared score parameters couple the species
-    with pytest.raises(bb.BiolithB200Error):
-        bb.fit(bb.models.occu_cs, **d2)
 
 
 class _D:

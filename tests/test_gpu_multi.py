@@ -13,6 +13,25 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    """A free port BELOW the ephemeral range: a port handed out by bind(0) can be taken by another process's outgoing
+    connection (e.g. an NCCL bootstrap socket) before the rendezvous store listens on it (seen once: EADDRINUSE)."""
+    import random
+
+    rng = random.Random(os.getpid() * 7919 + int.from_bytes(os.urandom(4), "little"))
+    for _ in range(200):
+        port = rng.randrange(21000, 31000)
+        s = socket.socket()
+        try:
+            s.bind(("127.0.0.1", port))
+            return port
+        except OSError:
+            continue
+        finally:
+            s.close()
+    raise RuntimeError("no free port")
+
+
 def _n_gpus():
     import ctypes as C
 
@@ -66,10 +85,7 @@ def test_site_sharded_ranks(mode, world):
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, mode, q)) for r in range(world)]
@@ -132,10 +148,7 @@ def test_hybrid_chains_by_sites_grid(mode):
         pytest.skip("needs 4 GPUs")
     import torch.multiprocessing as mp
 
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_hybrid_worker, args=(r, 4, port, mode, q)) for r in range(4)]

@@ -507,3 +507,84 @@ def test_full_size_site_split_additivity(model, sim_kw, model_kw):
     assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr))
     np.testing.assert_allclose(la.astype(np.float64) + lb, lp, rtol=5e-6)
     np.testing.assert_allclose(ga.astype(np.float64) + gb, gr, rtol=1e-4, atol=2e-5 * np.abs(gr).max())
+
+
+@pytest.mark.parametrize("name", ["occu_missing", "occu_5x3"])
+@pytest.mark.parametrize("dtype,tol", [("float32", 2e-5), ("float64", 3e-7)])  # outputs are float32
+def test_pointwise_loglik_against_the_reference_closed_form(name, dtype, tol):
+    """bl_obs_loglik vs numbers produced by EXECUTING the reference's log_likelihood_manual / lppd_manual
+    (biolith/evaluation/log_likelihood.py:55-98, lppd.py:64-106) on the deterministic sites of the executed occu body
+    (tests/golden/manual_refbody.npz): per-observation log-mean-exp, its variance over draws, and the lppd total."""
+    import os
+
+    from conftest import GOLDEN_DIR
+
+    g = load_golden(name)
+    m = np.load(os.path.join(GOLDEN_DIR, "manual_refbody.npz"))
+    llm = m[f"{name}__log_lik_manual"][:, 0]          # (draws, S, P, J), NaN where obs is NaN
+    with _make(g, dtype, prior=False) as lk:
+        out = lk.pointwise_loglik(g["thetas"])
+        mask = lk.mask()
+    n = llm.shape[0]
+    mx = np.nanmax(llm, axis=0)
+    ref_lppd = mx + np.log(np.exp(llm - mx).sum(axis=0) / n)
+    ref_var = llm.var(axis=0, ddof=1)
+    assert np.array_equal(np.isfinite(out["lppd"]), mask)
+    np.testing.assert_allclose(out["lppd"][mask], ref_lppd[mask], rtol=tol, atol=tol)
+    np.testing.assert_allclose(out["p_waic"][mask], ref_var[mask], rtol=200 * tol, atol=tol)
+    assert abs(out["lppd_total"] - float(m[f"{name}__lppd_manual"])) <= 10 * tol * abs(float(m[f"{name}__lppd_manual"]))
+
+
+@pytest.mark.parametrize("tag,model,extra,flags", [
+    ("occu_sp2_fpc", "occu", "prob_fp_constant", dict(false_positives_constant=True)),
+    ("occu_p2_sp3", "occu", None, {}),
+    ("cop_sp2_fpu", "occu_cop", "rate_fp_unoccupied", dict(false_positives_unoccupied=True)),
+])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_multi_species_against_the_executed_reference_body(tag, model, extra, flags, dtype):
+    """n_species > 1 with a false-positive parameter shared across the species plate (occu.py:146-157 sampled outside
+    occu.py:182): the composite handle (csrc/multi.cu) against the executed reference body -- log joint, every
+    species' beta / alpha gradient, and the gradient of the shared extra (a sum over species)."""
+    import os
+
+    import biolith_b200 as bb
+    from conftest import GOLDEN_DIR
+
+    e = dict(np.load(os.path.join(GOLDEN_DIR, "extra_refbody.npz")))
+    X, W, y = (e[f"{tag}__data__{k}"] for k in ("site_covs", "obs_covs", "obs"))
+    T = e.get(f"{tag}__data__session_duration")
+    tol = 1e-5 if dtype == "float32" else 1e-10
+    n = e[f"{tag}__logp"].size
+    th, gref = [], []
+    for i in range(n):
+        parts = [e[f"{tag}__param__beta"][i].ravel(), e[f"{tag}__param__alpha"][i].ravel()]
+        gparts = [e[f"{tag}__grad__beta"][i].ravel(), e[f"{tag}__grad__alpha"][i].ravel()]
+        if extra:
+            parts.append(np.atleast_1d(e[f"{tag}__param__{extra}"][i]))
+            gparts.append(np.atleast_1d(e[f"{tag}__grad__{extra}"][i]))
+        th.append(np.concatenate(parts))
+        gref.append(np.concatenate(gparts))
+    th, gref = np.stack(th), np.stack(gref)
+    # the fixtures were generated with float64 data and float64 clamp constants; fp32 runs see rounded data
+    with bb.OccupancyLikelihood(model, X, W, y, T, dtype=dtype, prior=True, **flags) as lk:
+        assert lk.n_species == y.shape[0] and lk.theta_dim == th.shape[1]
+        lp, gr = lk.logp_and_grad(th)
+        assert lk.mask().shape == y.shape
+    assert_close(lp, gr, e[f"{tag}__logp"], gref, tol if dtype == "float64" else 3e-5, f"{tag}/{dtype}")
+
+
+def test_fit_two_species_with_a_shared_false_positive_parameter():
+    """fit() on two species that share prob_fp_constant: one joint NUTS run over the composite handle; sample sites
+    have numpyro's plate layout (beta: (draws, n_species, Kb))."""
+    import biolith_b200 as bb
+    from biolith_b200.simulate import simulate_occupancy
+
+    data, true = simulate_occupancy("occu", n_species=2, n_sites=300, deployment_days_per_site=70,
+                                    prob_fp_constant=0.05, random_seed=1)
+    res = bb.fit(bb.models.occu, data["site_covs"], data["obs_covs"], data["obs"], num_chains=8, num_warmup=300,
+                 num_samples=200, false_positives_constant=True)
+    smp = res.samples
+    assert smp["cov_state_0"].shape == (8 * 200, 2) and smp["prob_fp_constant"].shape == (8 * 200,)
+    assert smp["psi"].shape[-1] == 2
+    assert abs(smp["prob_fp_constant"].mean() - 0.05) < 0.05
+    np.testing.assert_allclose(smp["cov_state_0"].mean(axis=0), true["beta"][:, 0], atol=0.6)

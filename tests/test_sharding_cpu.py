@@ -11,6 +11,25 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    """A free port BELOW the ephemeral range: a port handed out by bind(0) can be taken by another process's outgoing
+    connection (e.g. an NCCL bootstrap socket) before the rendezvous store listens on it (seen once: EADDRINUSE)."""
+    import random
+
+    rng = random.Random(os.getpid() * 7919 + int.from_bytes(os.urandom(4), "little"))
+    for _ in range(200):
+        port = rng.randrange(21000, 31000)
+        s = socket.socket()
+        try:
+            s.bind(("127.0.0.1", port))
+            return port
+        except OSError:
+            continue
+        finally:
+            s.close()
+    raise RuntimeError("no free port")
+
+
 def test_shard_ranges_partition_the_sites():
     from biolith_b200.sharded import shard_data, shard_range
 
@@ -52,10 +71,7 @@ def _worker(rank, world, port, q):
 def test_gloo_world2_exchange_and_gather():
     import torch.multiprocessing as mp
 
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
@@ -112,10 +128,7 @@ def _hybrid_worker(rank, world, port, q):
 def test_gloo_world4_hybrid_subgroups():
     import torch.multiprocessing as mp
 
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_hybrid_worker, args=(r, 4, port, q)) for r in range(4)]
