@@ -92,7 +92,9 @@ def test_unsupported_options_raise():
 
     data, _ = bb.simulate_occupancy("occu", random_seed=0)
     with pytest.raises(bb.BiolithB200Error):
-        bb.fit(bb.models.occu, **data, site_random_effects=True)
+        bb.fit(bb.models.occu, **data, coords=np.zeros((100, 2)))
+    with pytest.raises(bb.BiolithB200Error):
+        bb.fit(bb.models.occu_rn, **data, site_random_effects=True)  # random effects: occu only
     with pytest.raises(bb.BiolithB200Error):
         bb.fit(bb.models.occu, **data, kernel="hmc")
 
@@ -109,8 +111,9 @@ def test_fit_multi_season_and_multi_species_like_reference_tests():
     res = bb.fit(bb.models.occu, **data, num_chains=2, num_samples=100, num_warmup=100, timeout=600)
     assert res.samples["psi"].shape[-1] == 2
     assert res.samples["cov_state_0"].shape == (200, 2)
-    with pytest.raises(bb.BiolithB200Error):
-        bb.fit(bb.models.occu, **data, false_positives_constant=True)
+    # a shared false-positive parameter couples the species: one joint run over the composite handle
+    res = bb.fit(bb.models.occu, **data, num_chains=2, num_samples=50, num_warmup=50, false_positives_constant=True)
+    assert res.samples["cov_state_0"].shape == (100, 2) and res.samples["prob_fp_constant"].shape == (100,)
 
 
 def test_fit_nmixture_recovers_truth():
