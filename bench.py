@@ -426,10 +426,11 @@ def main():
 # They turn a measured time into an achieved issue / SFU rate; the peaks are measured by bl_pipe_peak.
 PROFILED = {
     # workload: (warp-instructions per (unit, chain) x 32 lanes -> per lane, MUFU per (unit, chain), DRAM bytes / launch, source)
-    # K1d (csrc/occu_signed.cu): 293.30 MB read + 6.99 MB written per launch (signed records: 176 MB packed)
-    "occu_1m_x8_c1024": dict(instr=190.7, mufu=18.1, traffic=300_288_512, src="profiles/r02_occu_signed_v2.txt"),
+    # K1d (csrc/occu_signed.cu): 268.49 MB read + 7.31 MB written per launch (signed records: 176 MB packed)
+    "occu_1m_x8_c1024": dict(instr=198.8, mufu=15.1, traffic=275_796_480, src="profiles/r02_occu_signed_final.txt"),
     "occu_cop_500k_x12": dict(instr=368.0, mufu=44.0, traffic=None, src="profiles/r01_occu_cop_chain_v1.txt"),
-    "occu_rn_200k_x10_k50": dict(instr=14886.0, mufu=None, traffic=None, src="profiles/r01_occu_rn_chain_v2.txt"),
+    # K2d (csrc/occu_rn2.cu): 41.80 MB read + 0.38 MB written per launch
+    "occu_rn_200k_x10_k50": dict(instr=4816.3, mufu=152.0, traffic=42_176_512, src="profiles/r02_occu_rn2_final.txt"),
 }
 _PIPE_PEAKS = {}
 
