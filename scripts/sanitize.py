@@ -8,7 +8,7 @@ import biolith_b200 as bb
 rng = np.random.default_rng(0)
 ALL = {"occu": {}, "occu_rn": dict(max_abundance=12), "occu_cop": dict(false_positives_constant=True),
        "nmixture": dict(max_abundance=80), "occu_cs": {}}
-todo = sys.argv[1:] or list(ALL)
+todo = [m for m in sys.argv[1:] if m in ALL] or ([] if sys.argv[1:] else list(ALL))
 S = int(os.environ.get("SANITIZE_SITES", "333"))
 for model in todo:
     kw = ALL[model]
@@ -25,3 +25,21 @@ for model in todo:
         s.run(max_steps=200)
         s.close()
     print(model, "ok", flush=True)
+if "extras" in sys.argv[1:] or not sys.argv[1:]:
+    # round 2: random effects (K9), composite species (K10), per-observation log-likelihood (K11)
+    data, _ = bb.simulate_occupancy("occu", n_site_covs=2, n_obs_covs=2, n_sites=S, n_species=2,
+                                    deployment_days_per_site=42, simulate_missing=True, random_seed=2)
+    one = data["obs"][:1]
+    with bb.OccupancyLikelihood("occu", data["site_covs"], data["obs_covs"], one, site_random_effects=True,
+                                obs_random_effects=True) as lk:
+        lp, gr = lk.logp_and_grad(0.3 * rng.standard_normal((5, lk.theta_dim)))
+        assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr))
+    with bb.OccupancyLikelihood("occu", data["site_covs"], data["obs_covs"], data["obs"],
+                                false_positives_constant=True) as lk:
+        for C in (3, 40):
+            lp, gr = lk.logp_and_grad(rng.uniform(-1, 1, size=(C, lk.theta_dim)))
+            assert np.all(np.isfinite(lp)) and np.all(np.isfinite(gr))
+    with bb.OccupancyLikelihood("occu", data["site_covs"], data["obs_covs"], one) as lk:
+        out = lk.pointwise_loglik(rng.uniform(-1, 1, size=(70, lk.theta_dim)))
+        assert np.isfinite(out["lppd_total"])
+    print("extras ok", flush=True)
