@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr", *os.environ.get("BL_EXTRA_NVCC_FLAGS", "").split(),
 ]
-SOURCES = ["api.cu", "pack.cu", "occu.cu", "occu_chain.cu", "occu_signed.cu", "occu_rn.cu", "occu_rn2.cu", "occu_re.cu", "obs_loglik.cu", "multi.cu", "occu_cop.cu", "nmixture.cu", "occu_cs.cu", "comm.cu", "nuts.cu", "xla.cu", "microbench.cu"]
+SOURCES = ["api.cu", "pack.cu", "occu.cu", "occu_chain.cu", "occu_signed.cu", "occu_small.cu", "occu_rn.cu", "occu_rn2.cu", "occu_re.cu", "obs_loglik.cu", "multi.cu", "occu_cop.cu", "nmixture.cu", "occu_cs.cu", "comm.cu", "nuts.cu", "xla.cu", "microbench.cu"]
 
 
 def _sources():

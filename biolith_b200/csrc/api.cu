@@ -58,6 +58,13 @@ int occu_signed_block_threads(int C);
 int64_t occu_signed_block_tiles(const Layout& L);
 cudaError_t launch_repack_signed(const void* packed, void* out, const Layout& L, cudaStream_t st);
 cudaError_t launch_occu_signed(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
+bool occu_small_supported(int dtype, int ks, int ko, uint32_t flags);
+int occu_small_max_chains();
+int occu_small_block_threads();
+int occu_small_blocks_per_sm(int CB);
+int64_t occu_small_block_tiles(const Layout& L);
+size_t occu_small_smem(const Layout& L, int nstage);
+cudaError_t launch_occu_small(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 bool occu_rn2_supported(int dtype, int ks, int ko, int J, int K, uint32_t flags);
 size_t occu_rn2_bytes(const Layout& L);
 size_t occu_rn2_smem(const Layout& L, int nstage, int K, int bt);
@@ -186,7 +193,24 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     if (want_chain && C >= 64 && ds->desc.model == BL_MODEL_OCCU_CS &&
         occu_cs_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags))
       pl.chain_kernel = 4;
-    if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
+    // occu below the chain kernels' threshold: K1s (lane = site, register-resident sums of <= 8 chains per block)
+    if (!want_chain && C < chain_min && !ds->force_engine && !extra && ds->desc.model == BL_MODEL_OCCU &&
+        occu_small_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags)) {
+      pl.chain_kernel = 7;
+      const int ncmax = occu_small_max_chains();
+      pl.chain_bt = occu_small_block_threads();
+      pl.chain_variant = 0;
+      pl.g.n_chunks = (C + ncmax - 1) / ncmax;
+      pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
+      pl.g.WS = pl.chain_bt / kWarp; pl.g.WC = 1;
+      pl.g.n_block_tiles = occu_small_block_tiles(ds->L);
+      pl.g.nstage = kMaxStages;
+      const size_t budget = ds->smem_limit / occu_small_blocks_per_sm(pl.g.CB) - 6 * 1024;  // static smem + reserve
+      while (pl.g.nstage > 2 && occu_small_smem(ds->L, pl.g.nstage) > budget) --pl.g.nstage;
+      pl.g.smem_bytes = occu_small_smem(ds->L, pl.g.nstage);
+      if (pl.g.smem_bytes + 8 * 1024 > ds->smem_limit) pl.chain_kernel = 0;  // very wide units: the engine
+      if (pl.chain_kernel == 0) pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit, 0);
+    } else if (pl.chain_kernel) {  // lane = chain: one warp-tile per stage, no theta / accumulator staging
       const int bt = pl.chain_kernel == 1   ? occu_chain_block_threads(ds->L.ks, ds->L.ko, C)
                      : pl.chain_kernel == 5 ? occu_signed_block_threads(C)
                      : pl.chain_kernel == 6 ? occu_rn2_block_threads(ds->L, C, ds->desc.max_abundance, ds->smem_limit)
@@ -231,6 +255,7 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     p.chain_bt = pl.chain_bt;
     p.chain_variant = pl.chain_variant;
     p.nch = pl.nch;
+    p.CB = pl.g.CB;  // K1s picks its instantiation by the chains per block
     int occ = 0;
     cudaError_t e = pl.chain_kernel == 1   ? launch_occu_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 5 ? launch_occu_signed(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
@@ -238,6 +263,7 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
                     : pl.chain_kernel == 2 ? launch_occu_rn_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 3 ? launch_occu_cop_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                     : pl.chain_kernel == 4 ? launch_occu_cs_chain(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
+                    : pl.chain_kernel == 7 ? launch_occu_small(p, dim3(1), pl.g.smem_bytes, nullptr, &occ)
                                            : launch_model(ds, p, dim3(1), pl.g.smem_bytes, nullptr, &occ);
     if (e != cudaSuccess) return fail(BL_ERR_CUDA, "occupancy query: %s", cudaGetErrorString(e));
     if (occ < 1) return fail(BL_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu B)", pl.g.smem_bytes);
@@ -360,6 +386,7 @@ int eval_device(bl_dataset* ds, const void* theta, int C, void* logp, void* grad
                   : pl->chain_kernel == 2 ? launch_occu_rn_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 3 ? launch_occu_cop_chain(p, grid, pl->g.smem_bytes, st, nullptr)
                   : pl->chain_kernel == 4 ? launch_occu_cs_chain(p, grid, pl->g.smem_bytes, st, nullptr)
+                  : pl->chain_kernel == 7 ? launch_occu_small(p, grid, pl->g.smem_bytes, st, nullptr)
                                           : launch_model(ds, p, grid, pl->g.smem_bytes, st, nullptr);
   if (e != cudaSuccess) return fail(BL_ERR_CUDA, "eval launch: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -1,4 +1,5 @@
-"""A few evaluations at C = 1 and C = 5 (config 2) for an ncu capture of the small-batch engine."""
+"""A few evaluations at C = 1 and C = 5 (config 2) for an ncu capture of the small-batch kernel (K1s, occu_small.cu;
+BL_SMALL_KERNEL=0: the site-parallel engine)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
