@@ -134,6 +134,8 @@ static void fill_params(const bl_dataset* ds, EvalParams& p) {
   p.nch = 4;
   p.coop_reduce = 1;
   if (const char* ev = getenv("BL_COOP_REDUCE")) p.coop_reduce = atoi(ev) != 0;
+  p.hier_reduce = 1;
+  if (const char* ev = getenv("BL_HIER_REDUCE")) p.hier_reduce = atoi(ev) != 0;
 }
 
 // geometry for C chains (cached); grows the fp64 partial workspace when needed
@@ -291,9 +293,10 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
     }
     if ((size_t)pl.g.n_chunks > ds->counters_cap) {
       cudaFree(ds->counters);
-      size_t n = (size_t)pl.g.n_chunks + 16;
-      if (cudaMalloc(&ds->counters, n * sizeof(unsigned int)) != cudaSuccess) return fail(BL_ERR_NOMEM, "counters");
-      cudaMemset(ds->counters, 0, n * sizeof(unsigned int));
+      size_t n = (size_t)pl.g.n_chunks + 16;  // kTicketStride tickets per chunk (final + group tickets, engine.cuh)
+      if (cudaMalloc(&ds->counters, n * kTicketStride * sizeof(unsigned int)) != cudaSuccess)
+        return fail(BL_ERR_NOMEM, "counters");
+      cudaMemset(ds->counters, 0, n * kTicketStride * sizeof(unsigned int));
       ds->counters_cap = n;
     }
     if (rn_need > ds->rn_scratch_cap) {

@@ -334,6 +334,7 @@ struct EvalParams {
   int chain_bt;   // lane = chain kernels: threads (= chains) per block of the selected variant
   int nch;        // engine: chains a warp interleaves per pass over a warp-tile (1, 2 or 4)
   int coop_reduce;  // last-block reduction: 1 = one warp per (chain, quantity) when there are <= 64 of them
+  int hier_reduce;  // 1 = two-level (group, then chunk) reduction of the site splits when there are >= 64 of them
   int allreduce;  // 0 none; 1 = leave raw sums in `sums` for a collective, finalize separately
   double* sums;   // [C][NQ] raw (un-prior'd) sums when allreduce != 0
 };

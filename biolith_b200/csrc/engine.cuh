@@ -120,19 +120,71 @@ __global__ void finalize_kernel(EvalParams p) {
 
 // Called by every thread of a block after it has published its [bx][c][q] partials: the last block
 // of the chain chunk (ticket counter) sums the site splits in split order and writes the outputs.
+//
+// Tickets of chunk y live at counters[y * kTicketStride + ...]: [0] the chunk's final ticket, [1 + g] group g's.
+// With >= kHierMinSplits site splits the sum is taken in TWO levels (measured on B200 at config 2, K1s: one block
+// walking 444..592 splits x (chains x quantities) through L2 on its own was 15 of 37 us at C = 1 and 29 of 78 us at
+// C = 5 -- every other SM idle): splits are cut into groups of ~sqrt(nsplit) consecutive blocks; the last block of
+// a group to arrive adds the group's rows (<= gs independent L2 loads per item, in flight together) IN PLACE into
+// the group's first row, then takes the chunk's final ticket; the last group adds the <= 63 group rows and
+// finalises.  Group membership and both summation orders are fixed by (grid, block index): deterministic.
+constexpr int kTicketStride = 64;
+constexpr unsigned kHierMinSplits = 64;
+
 template <typename T>
 __device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int ncb, int* s_is_last) {
   const int tid = threadIdx.x, NQ = p.NQ;
+  unsigned int* tickets = p.counters + (size_t)blockIdx.y * kTicketStride;
+  const int items = ncb * NQ;
+  const unsigned nsplit = gridDim.x;
+  if (p.hier_reduce && nsplit >= kHierMinSplits) {
+    unsigned gs = 16;
+    while (gs * gs < nsplit) ++gs;  // <= 63 groups for any grid up to 3969 splits
+    const unsigned ngroups = (nsplit + gs - 1) / gs;
+    const unsigned g = blockIdx.x / gs, gfirst = g * gs;
+    const unsigned gcount = min(gs, nsplit - gfirst);
+    const size_t rstride = (size_t)p.C * NQ;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_is_last = (atomicAdd(&tickets[1 + g], 1u) == gcount - 1);
+    __syncthreads();
+    if (!*s_is_last) return;
+    __threadfence();
+    double* row0 = p.partial + (size_t)gfirst * rstride + (size_t)c0 * NQ;
+    for (int i = tid; i < items; i += blockDim.x) {
+      double total = 0.0;
+#pragma unroll 8
+      for (unsigned b = 0; b < gcount; ++b) total += __ldcg(row0 + (size_t)b * rstride + i);
+      row0[i] = total;
+    }
+    if (tid == 0) tickets[1 + g] = 0;  // self-reset for the next launch
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_is_last = (atomicAdd(&tickets[0], 1u) == ngroups - 1);
+    __syncthreads();
+    if (!*s_is_last) return;
+    __threadfence();
+    const double* col0 = p.partial + (size_t)c0 * NQ;
+    for (int i = tid; i < items; i += blockDim.x) {
+      double total = 0.0;
+#pragma unroll 8
+      for (unsigned g2 = 0; g2 < ngroups; ++g2) total += __ldcg(col0 + (size_t)g2 * gs * rstride + i);
+      const int c = c0 + i / NQ, q = i % NQ;
+      if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
+      else finalize_chain<T>(p, c, q, total, true);
+    }
+    if (tid == 0) tickets[0] = 0;
+    return;
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const unsigned int ticket = atomicAdd(&p.counters[blockIdx.y], 1u);
+    const unsigned int ticket = atomicAdd(&tickets[0], 1u);
     *s_is_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
   if (!*s_is_last) return;
   __threadfence();
-  const int items = ncb * NQ;
   // measured (config 2, us per evaluation, thread-per-item / warp-per-item): C=1 (11 items) 45.8 / 41.6, C=2 63.4 / 63.1,
   // C=4 (44 items) 90.1 / 99.5, C=5 110.6 / 126.5 -> cooperative only up to 32 items
   constexpr int kCoopItems = 32;
@@ -167,7 +219,7 @@ __device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int nc
       else finalize_chain<T>(p, c, q, total, true);
     }
   }
-  if (tid == 0) p.counters[blockIdx.y] = 0;  // self-reset for the next launch
+  if (tid == 0) tickets[0] = 0;  // self-reset for the next launch
 }
 
 // Sums q[0..NQ) of one (warp-tile, chain) over the 32 lanes into the warp's fp64 accumulator row, in

@@ -57,6 +57,8 @@ def f32(d):
 data, truth = bb.simulate_occupancy("occu", n_site_covs=5, n_obs_covs=3, n_sites=S, deployment_days_per_site=56)
 data = f32(data)
 sweep("config2 U(-2,2)", data, oracle_chains=3)
+if len(sys.argv) > 2:  # quick: the first sweep only
+    sys.exit(0)
 sweep("config2 near truth", data, oracle_chains=3,
       mode_theta=np.concatenate([truth["beta"][0], truth["alpha"][0]]).astype(np.float32), engine=False)
 data2, _ = bb.simulate_occupancy("occu", n_site_covs=2, n_obs_covs=2, n_sites=S, deployment_days_per_site=35,
