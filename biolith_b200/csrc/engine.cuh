@@ -64,13 +64,15 @@ __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, 
     double lp = total + (add_const ? p.cop_const : 0.0);
     if (prior) {
       const double h2pi = 0.91893853320467274178;  // 0.5*log(2*pi)
+      const double nb = log(p.prior_beta_scale) + h2pi, na = log(p.prior_alpha_scale) + h2pi;  // once, not per term
+      const double ib = 1.0 / p.prior_beta_scale, ia = 1.0 / p.prior_alpha_scale;
       for (int i = 0; i < KB; ++i) {
-        double z = ((double)theta[i] - p.prior_beta_loc) / p.prior_beta_scale;
-        lp += -0.5 * z * z - log(p.prior_beta_scale) - h2pi;
+        const double z = ((double)theta[i] - p.prior_beta_loc) * ib;
+        lp += -0.5 * z * z - nb;
       }
       for (int i = 0; i < KA; ++i) {
-        double z = ((double)theta[KB + i] - p.prior_alpha_loc) / p.prior_alpha_scale;
-        lp += -0.5 * z * z - log(p.prior_alpha_scale) - h2pi;
+        const double z = ((double)theta[KB + i] - p.prior_alpha_loc) * ia;
+        lp += -0.5 * z * z - na;
       }
       if (p.model == BL_MODEL_OCCU_CS) {
         const double x[4] = {(double)theta[KB + KA], (double)theta[KB + KA + 1], (double)theta[KB + KA + 2],

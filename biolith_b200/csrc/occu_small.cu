@@ -146,20 +146,32 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
   __shared__ int s_is_last;
   __shared__ __align__(16) float s_th[kSmallMaxNC * kSmallThetaStride];
   __shared__ double s_red[kSmallWarps][kSmallMaxNC][1 + 16];
-  const uint32_t tile_elems = (uint32_t)kSmallWarps * F * kWarp;
+  // one TMA ring PER WARP (warp-tile = 32 sites = F x 128 B, one cp.async.bulk each): no block barrier in the loop,
+  // the warps drift freely (measured with a block-wide ring and one barrier per 4 warp-tiles: barrier stalls 0.65
+  // per issue at C = 5)
+  const uint32_t tile_elems = (uint32_t)F * kWarp;
   const uint32_t tile_bytes = tile_elems * sizeof(float);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = blockIdx.y * p.CB;
   const int ncb = min(p.CB, p.C - c0);
-  const int64_t nbt = p.n_block_tiles;
-  const int64_t bt_begin = nbt * blockIdx.x / gridDim.x;
-  const int64_t bt_end = nbt * (blockIdx.x + 1) / gridDim.x;
-  const int n_it = (int)(bt_end - bt_begin);
-  const float* packed = reinterpret_cast<const float*>(p.packed);
+  const int64_t nwt = p.L.n_tiles;
+  const int64_t wt_begin = nwt * blockIdx.x / gridDim.x;
+  const int64_t wt_end = nwt * (blockIdx.x + 1) / gridDim.x;
+  const int64_t wt_mine = wt_end - wt_begin - warp;  // this warp takes wt_begin + warp, + 4, + 8, ...
+  const int n_it = wt_mine > 0 ? (int)((wt_mine + kSmallWarps - 1) / kSmallWarps) : 0;
+  const float* packed = reinterpret_cast<const float*>(p.packed) + (size_t)(wt_begin + warp) * tile_elems;
+  constexpr size_t kStep = kSmallWarps;  // warp-tiles between two iterations of a warp
+  uint64_t* wbars = bars + warp * kMaxStages;
+  float* wstage0 = stage0 + (size_t)warp * p.nstage * tile_elems;
 
-  if (tid == 0) {
-    for (int s = 0; s < p.nstage; ++s) mbar_init(&bars[s], 1);
+  if (lane == 0) {  // the data does not depend on theta: start the copies before anything else
+    for (int s = 0; s < p.nstage; ++s) mbar_init(&wbars[s], 1);
     fence_mbar_init();
+    const int pre = min(p.nstage, n_it);
+    for (int s = 0; s < pre; ++s) {
+      mbar_expect_tx(&wbars[s], tile_bytes);
+      tma_load_bulk(wstage0 + (size_t)s * tile_elems, packed + (size_t)s * kStep * tile_elems, tile_bytes, &wbars[s]);
+    }
   }
   for (int i = tid; i < NC * kSmallThetaStride; i += kSmallBT) {
     const int c = i / kSmallThetaStride, e = i % kSmallThetaStride;
@@ -171,15 +183,7 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
     }
     s_th[i] = v;
   }
-  __syncthreads();
-  if (tid == 0) {
-    const int pre = min(p.nstage, n_it);
-    for (int s = 0; s < pre; ++s) {
-      mbar_expect_tx(&bars[s], tile_bytes);
-      tma_load_bulk(stage0 + (size_t)s * tile_elems, packed + (size_t)(bt_begin + s) * tile_elems, tile_bytes,
-                    &bars[s]);
-    }
-  }
+  __syncthreads();  // theta staged, every warp's barriers initialised
   const float log_tiny = Num<float>::log_tiny();
   const int nq = (J + 3) / 4;
 
@@ -194,9 +198,9 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
 
   for (int it = 0; it < n_it; ++it) {
     const int st = it % p.nstage;
-    mbar_wait(&bars[st], (uint32_t)((it / p.nstage) & 1));
-    const float* tile = stage0 + (size_t)st * tile_elems + (size_t)warp * F * kWarp;
-    const int64_t unit = ((bt_begin + it) * kSmallWarps + warp) * kWarp + lane;
+    mbar_wait(&wbars[st], (uint32_t)((it / p.nstage) & 1));
+    const float* tile = wstage0 + (size_t)st * tile_elems;
+    const int64_t unit = (wt_begin + warp + (int64_t)it * kSmallWarps) * kWarp + lane;
     const float vf = unit < p.L.n_units ? 1.f : 0.f;
 
     float x[KSM];
@@ -295,11 +299,11 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
         for (int k = 0; k < KA; ++k) acc[c][KBM + k] = fmaf(r, ga[k], acc[c][KBM + k]);
       }
     }
-    __syncthreads();  // every warp is done reading stage st
-    if (tid == 0 && it + p.nstage < n_it) {
-      mbar_expect_tx(&bars[st], tile_bytes);
-      tma_load_bulk(stage0 + (size_t)st * tile_elems, packed + (size_t)(bt_begin + it + p.nstage) * tile_elems,
-                    tile_bytes, &bars[st]);
+    __syncwarp();  // every lane is done reading stage st
+    if (lane == 0 && it + p.nstage < n_it) {
+      mbar_expect_tx(&wbars[st], tile_bytes);
+      tma_load_bulk(wstage0 + (size_t)st * tile_elems, packed + (size_t)(it + p.nstage) * kStep * tile_elems, tile_bytes,
+                    &wbars[st]);
     }
   }
 
