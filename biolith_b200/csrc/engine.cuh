@@ -134,11 +134,44 @@ constexpr int kTicketStride = 64;
 constexpr unsigned kHierMinSplits = 64;
 
 template <typename T>
-__device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int ncb, int* s_is_last) {
+__device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int ncb, int* s_is_last,
+                                             double* coop_scratch = nullptr) {
   const int tid = threadIdx.x, NQ = p.NQ;
   unsigned int* tickets = p.counters + (size_t)blockIdx.y * kTicketStride;
   const int items = ncb * NQ;
   const unsigned nsplit = gridDim.x;
+  if (coop_scratch && items <= (int)blockDim.x && nsplit <= 256) {
+    // Few items, one block per SM (K1s; `coop_scratch` = blockDim.x doubles of shared memory): the last block sums
+    // with ALL its threads -- thread (g, j) adds rows g, g + G, ... of item j (G = blockDim.x / items; the loads of
+    // a thread are independent and in flight together), then thread j adds the G sums in order: one ticket, one or
+    // two L2 round trips, a fixed order.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *s_is_last = (atomicAdd(&tickets[0], 1u) == nsplit - 1);
+    __syncthreads();
+    if (!*s_is_last) return;
+    __threadfence();
+    const int G = (int)blockDim.x / items;
+    const size_t rstride = (size_t)p.C * NQ;
+    if (tid < G * items) {
+      const int g = tid / items, j = tid % items;
+      const double* src = p.partial + (size_t)c0 * NQ + j;
+      double total = 0.0;
+#pragma unroll 8
+      for (unsigned b = g; b < nsplit; b += G) total += __ldcg(src + (size_t)b * rstride);
+      coop_scratch[tid] = total;
+    }
+    __syncthreads();
+    if (tid < items) {
+      double total = 0.0;
+      for (int g = 0; g < G; ++g) total += coop_scratch[g * items + tid];
+      const int c = c0 + tid / NQ, q = tid % NQ;
+      if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
+      else finalize_chain<T>(p, c, q, total, true);
+    }
+    if (tid == 0) tickets[0] = 0;
+    return;
+  }
   if (p.hier_reduce && nsplit >= kHierMinSplits) {
     unsigned gs = 16;
     while (gs * gs < nsplit) ++gs;  // <= 63 groups for any grid up to 3969 splits

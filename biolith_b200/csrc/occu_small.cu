@@ -3,7 +3,8 @@
 //
 // The site-parallel engine (engine.cuh + occu.cu) pays, per (warp-tile, chain), a 16-shuffle transposed butterfly into
 // fp64 shared-memory accumulators and 3 MUFU per visit.  This kernel keeps the engine's packed "SoA in tile" dataset
-// (128 B / site at config 2 -- a second packing would cost the HBM-bound C = 1 case its bandwidth) and its TMA ring, but
+// (128 B / site at config 2 -- a second packing would cost the HBM-bound C = 1 case its bandwidth), staged by TMA
+// through one mbarrier ring PER WARP (no block barrier in the loop), but
 //   * holds the per-lane sums of a chunk of <= 8 chains in REGISTERS over every tile a thread walks and reduces them
 //     across lanes ONCE per block (fp32 over the <= ~20 sites of a lane, fp64 from there on): nothing per (tile, chain);
 //   * uses K1d's visit arithmetic (occu_signed.cu; reference: biolith/models/occu.py:221-242 with p_fp = z p):
@@ -23,8 +24,12 @@
 
 namespace bl {
 
-constexpr int kSmallBT = 128;                      // 4 warps = 4 warp-tiles per ring slot
-constexpr int kSmallWarps = kSmallBT / kWarp;
+// ONE block per SM, as many warps as the register file carries for NC chains (<= 2: 128 registers x 512 threads,
+// <= 5: 168 x 384, <= 8: 255 x 256): with a ring per warp the block size costs nothing in the loop, and the last-block
+// reduction sums 148 partial rows instead of 444..592 (measured with 128-thread blocks, 3..4 per SM: C = 1 34.4 us of
+// which 21.6 us streaming; the two-level sum of 592 rows was most of the rest).
+__host__ __device__ constexpr int small_bt(int nc) { return nc <= 2 ? 512 : (nc <= 5 ? 384 : 256); }
+constexpr int kSmallHeader = 512;                  // 16 warps x kMaxStages mbarriers
 constexpr int kSmallMaxNC = 8;                     // chains per block (register-resident sums)
 constexpr int kSmallMaxKs = 8;
 constexpr int kSmallThetaStride = 16;              // staged theta row: [beta (KBM) | alpha_0, alpha_1..KO], padded
@@ -132,8 +137,9 @@ __device__ __forceinline__ void small_decode(const float* __restrict__ tile, int
 
 // KS < 0: runtime Ks (<= kSmallMaxKs).  J8: the site's 8 visits are decoded once into registers (J == 8); otherwise
 // visits are decoded per chain from shared memory in quads (any J).
-template <int KS, int KO, bool J8, int NC, int MINB>
-__global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalParams p) {
+template <int KS, int KO, bool J8, int NC>
+__global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalParams p) {
+  constexpr int kSmallBT = small_bt(NC), kSmallWarps = kSmallBT / kWarp;
   constexpr int KSM = KS < 0 ? kSmallMaxKs : KS;
   constexpr int KBM = KSM + 1, KA = KO + 1, NG = KBM + KA;  // gradient slots in this kernel's (padded) order
   static_assert(NG <= 16 && KBM + KA <= kSmallThetaStride, "one 16-wide butterfly / theta row");
@@ -142,10 +148,11 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
   const int F = p.L.F, off_w = p.L.off_w, off_y = p.L.off_y, off_m = p.L.off_m;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
+  float* stage0 = reinterpret_cast<float*>(smem_raw + kSmallHeader);
   __shared__ int s_is_last;
-  __shared__ __align__(16) float s_th[kSmallMaxNC * kSmallThetaStride];
-  __shared__ double s_red[kSmallWarps][kSmallMaxNC][1 + 16];
+  __shared__ __align__(16) float s_th[NC * kSmallThetaStride];
+  __shared__ double s_red[kSmallWarps][NC][1 + 16];
+  __shared__ double s_scr[kSmallBT];  // scratch of the cooperative last-block reduction
   // one TMA ring PER WARP (warp-tile = 32 sites = F x 128 B, one cp.async.bulk each): no block barrier in the loop,
   // the warps drift freely (measured with a block-wide ring and one barrier per 4 warp-tiles: barrier stalls 0.65
   // per issue at C = 5)
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
   const int64_t nwt = p.L.n_tiles;
   const int64_t wt_begin = nwt * blockIdx.x / gridDim.x;
   const int64_t wt_end = nwt * (blockIdx.x + 1) / gridDim.x;
-  const int64_t wt_mine = wt_end - wt_begin - warp;  // this warp takes wt_begin + warp, + 4, + 8, ...
+  const int64_t wt_mine = wt_end - wt_begin - warp;  // this warp takes wt_begin + warp, + kSmallWarps, ...
   const int n_it = wt_mine > 0 ? (int)((wt_mine + kSmallWarps - 1) / kSmallWarps) : 0;
   const float* packed = reinterpret_cast<const float*>(p.packed) + (size_t)(wt_begin + warp) * tile_elems;
   constexpr size_t kStep = kSmallWarps;  // warp-tiles between two iterations of a warp
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kSmallBT, MINB) occu_small_kernel(const EvalPa
     for (int w = 0; w < kSmallWarps; ++w) v += s_red[w][c][slot];
     my_partial[i] = v;
   }
-  finish_block<float>(p, c0, ncb, &s_is_last);
+  finish_block<float>(p, c0, ncb, &s_is_last, s_scr);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -345,29 +352,23 @@ bool occu_small_supported(int dtype, int ks, int ko, uint32_t flags) {
 }
 
 int occu_small_max_chains() { return kSmallMaxNC; }
-int occu_small_block_threads() { return kSmallBT; }
-int64_t occu_small_block_tiles(const Layout& L) { return (L.n_tiles + kSmallWarps - 1) / kSmallWarps; }
+int occu_small_block_threads(int CB) { return small_bt(CB); }
 
-// resident blocks per SM the launch bounds ask for: few chains leave registers for more warps (latency hiding in
-// the HBM-bound regime); 6..8 chains need the whole 255-register budget
-static constexpr int small_minb(int nc) { return nc <= 2 ? 4 : (nc <= 5 ? 3 : 2); }
-int occu_small_blocks_per_sm(int CB) { return small_minb(CB); }
-
-size_t occu_small_smem(const Layout& L, int nstage) {
-  return 128 + (size_t)nstage * kSmallWarps * L.F * kWarp * sizeof(float);
+size_t occu_small_smem(const Layout& L, int nstage, int CB) {
+  return kSmallHeader + (size_t)nstage * (small_bt(CB) / kWarp) * L.F * kWarp * sizeof(float);
 }
 
 template <int KS, int KO, bool J8, int NC>
 static cudaError_t launch_small_one(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = occu_small_kernel<KS, KO, J8, NC, small_minb(NC)>;
+  auto kern = occu_small_kernel<KS, KO, J8, NC>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kSmallBT, smem);
-  kern<<<grid, kSmallBT, smem, st>>>(p);
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, small_bt(NC), smem);
+  kern<<<grid, small_bt(NC), smem, st>>>(p);
   return cudaGetLastError();
 }
 
