@@ -41,6 +41,20 @@ __device__ __forceinline__ float sm_exp_neg_abs(float x) {
   return sfu::ex2(fmaf(t, kSmLog2eLo, t * sfu::kLog2e));
 }
 
+#ifdef BL_TRACE
+// profiling aid (built only with -DBL_TRACE): five %globaltimer stamps per block -- entry, first tile landed (warp 0),
+// warp 0 done with its tiles, block partial published, block exit
+__device__ unsigned long long g_small_trace[8 * 2048];
+__device__ __forceinline__ unsigned long long small_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define BL_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 2048) g_small_trace[blockIdx.x * 8 + (i)] = small_now(); } while (0)
+#else
+#define BL_STAMP(i) do { } while (0)
+#endif
+
 template <int KO> struct SmallSlow { float L1; float ga[KO + 1]; };
 
 // exact per-visit form of one site for one chain (rare): numpyro's clamps through sfu::softsig<true>, natural units
@@ -171,6 +185,7 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
   uint64_t* wbars = bars + warp * kMaxStages;
   float* wstage0 = stage0 + (size_t)warp * p.nstage * tile_elems;
 
+  BL_STAMP(0);
   if (lane == 0) {  // the data does not depend on theta: start the copies before anything else
     for (int s = 0; s < p.nstage; ++s) mbar_init(&wbars[s], 1);
     fence_mbar_init();
@@ -206,6 +221,7 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
   for (int it = 0; it < n_it; ++it) {
     const int st = it % p.nstage;
     mbar_wait(&wbars[st], (uint32_t)((it / p.nstage) & 1));
+    if (it == 0) BL_STAMP(1);
     const float* tile = wstage0 + (size_t)st * tile_elems;
     const int64_t unit = (wt_begin + warp + (int64_t)it * kSmallWarps) * kWarp + lane;
     const float vf = unit < p.L.n_units ? 1.f : 0.f;
@@ -314,6 +330,7 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
     }
   }
 
+  BL_STAMP(2);
   // once per block: lanes -> warp (fixed butterfly), warps -> block (fixed order), publish [bx][c][q]
   const int NQ = p.NQ;
 #pragma unroll
@@ -339,8 +356,16 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
     for (int w = 0; w < kSmallWarps; ++w) v += s_red[w][c][slot];
     my_partial[i] = v;
   }
+  BL_STAMP(3);
   finish_block<float>(p, c0, ncb, &s_is_last, s_scr);
+  BL_STAMP(4);
 }
+
+#ifdef BL_TRACE
+extern "C" __attribute__((visibility("default"))) int bl_debug_small_trace(unsigned long long* out, int n_blocks) {
+  return (int)cudaMemcpyFromSymbol(out, g_small_trace, (size_t)n_blocks * 8 * sizeof(unsigned long long));
+}
+#endif
 
 // ---- host side ----------------------------------------------------------------------------------------------
 bool occu_small_supported(int dtype, int ks, int ko, uint32_t flags) {
