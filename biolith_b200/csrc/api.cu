@@ -1,5 +1,6 @@
 // C ABI of libbiolith_b200.so (declared in include/biolith_b200.h).  Plain pointers and sizes only.
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -126,6 +127,10 @@ static void fill_params(const bl_dataset* ds, EvalParams& p) {
   p.prior_beta_scale = ds->desc.prior_beta_scale;
   p.prior_alpha_loc = ds->desc.prior_alpha_loc;
   p.prior_alpha_scale = ds->desc.prior_alpha_scale;
+  p.prior_beta_norm = log(p.prior_beta_scale) + 0.91893853320467274178;
+  p.prior_alpha_norm = log(p.prior_alpha_scale) + 0.91893853320467274178;
+  p.prior_beta_iscale = 1.0 / p.prior_beta_scale;
+  p.prior_alpha_iscale = 1.0 / p.prior_alpha_scale;
   p.prior_fp_a = ds->desc.prior_fp_a;
   p.prior_fp_b = ds->desc.prior_fp_b;
   p.prior_fp_rate = ds->desc.prior_fp_rate;

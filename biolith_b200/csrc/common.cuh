@@ -329,6 +329,8 @@ struct EvalParams {
   void* rn_scratch_global;  // occu_rn: non-NULL -> A_k scratch in global memory (too big for smem)
   double cop_const;  // occu_cop: sum_s sum_j m (y log T - lgamma(y+1)), data-only
   double prior_beta_loc, prior_beta_scale, prior_alpha_loc, prior_alpha_scale;
+  double prior_beta_norm, prior_alpha_norm;      // log(scale) + 0.5 log(2 pi), computed on the host
+  double prior_beta_iscale, prior_alpha_iscale;  // 1 / scale
   double prior_fp_a, prior_fp_b, prior_fp_rate;
   int chain_variant;  // BL_CHAIN_VARIANT tuning switch as read at plan time (3 = runtime-J kernel)
   int chain_bt;   // lane = chain kernels: threads (= chains) per block of the selected variant

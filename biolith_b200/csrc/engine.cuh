@@ -64,8 +64,11 @@ __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, 
     double lp = total + (add_const ? p.cop_const : 0.0);
     if (prior) {
       const double h2pi = 0.91893853320467274178;  // 0.5*log(2*pi)
-      const double nb = log(p.prior_beta_scale) + h2pi, na = log(p.prior_alpha_scale) + h2pi;  // once, not per term
-      const double ib = 1.0 / p.prior_beta_scale, ia = 1.0 / p.prior_alpha_scale;
+      // log(scale) + 0.5 log(2 pi) and 1 / scale come from the host (fill_params): a serial fp64 log / division
+      // chain in the one thread every evaluation waits for
+      const double nb = p.prior_beta_norm, na = p.prior_alpha_norm;
+      const double ib = p.prior_beta_iscale, ia = p.prior_alpha_iscale;
+      (void)h2pi;
       for (int i = 0; i < KB; ++i) {
         const double z = ((double)theta[i] - p.prior_beta_loc) * ib;
         lp += -0.5 * z * z - nb;
@@ -96,8 +99,8 @@ __device__ void finalize_chain(const EvalParams& p, int c, int q, double total, 
     double g = total;
     if (prior) {
       double x = (double)theta[i];
-      if (i < KB) g -= (x - p.prior_beta_loc) / (p.prior_beta_scale * p.prior_beta_scale);
-      else if (i < KB + KA) g -= (x - p.prior_alpha_loc) / (p.prior_alpha_scale * p.prior_alpha_scale);
+      if (i < KB) g -= (x - p.prior_beta_loc) * (p.prior_beta_iscale * p.prior_beta_iscale);
+      else if (i < KB + KA) g -= (x - p.prior_alpha_loc) * (p.prior_alpha_iscale * p.prior_alpha_iscale);
       else if (p.model == BL_MODEL_OCCU_CS) {
         const double xe[4] = {(double)theta[KB + KA], (double)theta[KB + KA + 1], (double)theta[KB + KA + 2],
                               (double)theta[KB + KA + 3]};
@@ -177,7 +180,13 @@ __device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int nc
     __syncthreads();
     if (tid < items) {
       double total = 0.0;
-      for (int g = 0; g < G; ++g) total += coop_scratch[g * items + tid];
+      for (int g0 = 0; g0 < G; g0 += 16) {  // shared-memory reads in flight together, adds in index order
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = (g0 + u < G) ? coop_scratch[(g0 + u) * items + tid] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) total += v[u];
+      }
       const int c = c0 + tid / NQ, q = tid % NQ;
       if (p.allreduce) p.sums[(size_t)c * NQ + q] = total + (q == 0 ? p.cop_const : 0.0);
       else finalize_chain<T>(p, c, q, total, true);

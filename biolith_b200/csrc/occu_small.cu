@@ -189,10 +189,9 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
   if (lane == 0) {  // the data does not depend on theta: start the copies before anything else
     for (int s = 0; s < p.nstage; ++s) mbar_init(&wbars[s], 1);
     fence_mbar_init();
-    const int pre = min(p.nstage, n_it);
-    for (int s = 0; s < pre; ++s) {
-      mbar_expect_tx(&wbars[s], tile_bytes);
-      tma_load_bulk(wstage0 + (size_t)s * tile_elems, packed + (size_t)s * kStep * tile_elems, tile_bytes, &wbars[s]);
+    if (n_it > 0) {  // stage 0 of every warp first: the first tiles land ~2 us earlier than behind a full ring
+      mbar_expect_tx(&wbars[0], tile_bytes);
+      tma_load_bulk(wstage0, packed, tile_bytes, &wbars[0]);
     }
   }
   for (int i = tid; i < NC * kSmallThetaStride; i += kSmallBT) {
@@ -206,6 +205,13 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
     s_th[i] = v;
   }
   __syncthreads();  // theta staged, every warp's barriers initialised
+  if (lane == 0) {
+    const int pre = min(p.nstage, n_it);
+    for (int s = 1; s < pre; ++s) {
+      mbar_expect_tx(&wbars[s], tile_bytes);
+      tma_load_bulk(wstage0 + (size_t)s * tile_elems, packed + (size_t)s * kStep * tile_elems, tile_bytes, &wbars[s]);
+    }
+  }
   const float log_tiny = Num<float>::log_tiny();
   const int nq = (J + 3) / 4;
 
