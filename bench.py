@@ -379,6 +379,8 @@ def main():
             line["nuts"] = nuts
         if world == 1 and args.workload == "occu_1m_x8_c1024" and not args.no_other_workloads:
             line["other_workloads"] = other_workloads(lib, local_rank, args)
+        if world == 1 and model == "occu" and args.dtype == "float32" and not args.strict_math and not args.no_other_workloads:
+            line["small_batch"] = small_batch(lib, lk, local_rank)
         if world == 1 and model == "occu" and args.dtype == "float32" and not args.strict_math:
             # the same evaluation with libm expf / log1pf / IEEE division (BL_FLAG_STRICT_MATH), for the record:
             # the default kernels use bounded-error SFU forms (DESIGN.md "Numerics"); never fatal for the line
@@ -513,6 +515,32 @@ def _time_eval(lib, lk, theta, device, steps, warmup=3):
         b.free()
     lib.bl_stream_destroy(stream)
     return float(np.mean(ms))
+
+
+def small_batch(lib, lk, device):
+    """The same dataset evaluated for 1 and 5 chains (5 = the reference's default num_chains, utils/fit.py:24): the
+    regime that IS bound by HBM -- one pass over the packed dataset per evaluation, nothing to reuse a tile for --
+    so its roofline is bytes / time against the measured copy bandwidth (L2 flushed between steps)."""
+    out = {}
+    peak, src = measured_peak_hbm()
+    try:
+        for c in (1, 5):
+            theta = np.random.default_rng(2000 + c).uniform(-2, 2, size=(c, lk.theta_dim)).astype(np.float32)
+            ms = _time_eval(lib, lk, theta, device, steps=20, warmup=5)
+            plan = lk.plan(c)
+            gbs_alg = c * lk.algorithmic_bytes / (ms * 1e-3) / 1e9
+            gbs_phys = lk.packed_bytes / (ms * 1e-3) / 1e9
+            out[f"c{c}"] = {"chains": c, "us_per_eval": ms * 1e3, "value": c / (ms * 1e-3), "unit": UNIT,
+                            "kernel": plan["kernel"], "grid": list(plan["grid"]), "block_threads": plan["block_threads"],
+                            "roofline": {"bound": "hbm", "achieved": gbs_phys, "peak": peak, "unit": "GB/s",
+                                         "frac": gbs_phys / peak, "traffic": lk.packed_bytes,
+                                         "achieved_algorithmic": gbs_alg, "frac_algorithmic": gbs_alg / peak,
+                                         "peak_source": src,
+                                         "note": "achieved = packed dataset bytes (one pass, = ncu dram bytes read) / "
+                                                 "time; achieved_algorithmic = chains x SURVEY 8d bytes / time"}}
+    except Exception as exc:  # noqa: BLE001 - never fatal for the headline line
+        out["error"] = str(exc)[:300]
+    return out
 
 
 def other_workloads(lib, device, args):

@@ -69,6 +69,8 @@ SIGNATURES = {
     "bl_dataset_create": (C.c_int, [C.POINTER(bl_desc), _P, _P, _P, _P, C.POINTER(_P)]),
     "bl_dataset_destroy": (C.c_int, [_P]),
     "bl_dataset_info": (C.c_int, [_P, C.POINTER(bl_info)]),
+    "bl_plan_kernel": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32)]),
     "bl_dataset_export_mask": (C.c_int, [_P, _P]),
     "bl_eval": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "bl_eval_host": (C.c_int, [_P, _P, C.c_int32, _P, _P]),

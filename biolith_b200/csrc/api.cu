@@ -137,6 +137,8 @@ static void fill_params(const bl_dataset* ds, EvalParams& p) {
   p.nch = 4;
   p.coop_reduce = 1;
   if (const char* ev = getenv("BL_COOP_REDUCE")) p.coop_reduce = atoi(ev) != 0;
+  p.ring_mode = 0;
+  if (const char* ev = getenv("BL_SIGNED_RING")) p.ring_mode = atoi(ev);
   p.hier_reduce = 1;
   if (const char* ev = getenv("BL_HIER_REDUCE")) p.hier_reduce = atoi(ev) != 0;
 }
@@ -675,6 +677,21 @@ int bl_dataset_info(const bl_dataset* ds, bl_info* info) {
   const bool fp = ds->n_extras > 0;
   info->kernel_variant = ds->desc.model == BL_MODEL_OCCU ? occu_has_specialisation(L.ks, L.ko, fp)
                          : ds->desc.model == BL_MODEL_OCCU_CS ? occu_cs_has_specialisation(L.ks, L.ko) : 0;
+  return BL_OK;
+}
+
+int bl_plan_kernel(bl_dataset* ds, int32_t n_chains, int32_t* kernel_id, int32_t* grid_x, int32_t* grid_y,
+                   int32_t* block_threads) {
+  if (!ds || !kernel_id || n_chains < 1) return fail(BL_ERR_INVALID, "bad argument");
+  if (!ds->species.empty() || ds->re) return fail(BL_ERR_UNSUPPORTED, "composite / random-effects handles plan per child");
+  CU_TRY(cudaSetDevice(ds->desc.device));
+  Plan* pl = nullptr;
+  const int rc = plan_for(ds, n_chains, &pl);
+  if (rc) return rc;
+  *kernel_id = pl->chain_kernel;
+  if (grid_x) *grid_x = pl->g.nsplit;
+  if (grid_y) *grid_y = pl->g.n_chunks;
+  if (block_threads) *block_threads = pl->chain_kernel ? pl->chain_bt : kBlockThreads;
   return BL_OK;
 }
 

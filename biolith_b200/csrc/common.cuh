@@ -287,6 +287,9 @@ __device__ __forceinline__ void tma_load_bulk(void* dst_smem, const void* src_gm
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   const uint32_t a = smem_u32(bar);
@@ -336,6 +339,7 @@ struct EvalParams {
   int chain_bt;   // lane = chain kernels: threads (= chains) per block of the selected variant
   int nch;        // engine: chains a warp interleaves per pass over a warp-tile (1, 2 or 4)
   int coop_reduce;  // last-block reduction: 1 = one warp per (chain, quantity) when there are <= 64 of them
+  int ring_mode;    // K1d: 0 = block barrier per ring slot; 1 = consumers release slots through `empty` mbarriers
   int hier_reduce;  // 1 = two-level (group, then chunk) reduction of the site splits when there are >= 64 of them
   int allreduce;  // 0 none; 1 = leave raw sums in `sums` for a collective, finalize separately
   double* sums;   // [C][NQ] raw (un-prior'd) sums when allreduce != 0

@@ -257,8 +257,15 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
   const int n_it = (int)(bt_end - bt_begin);
   const float* packed = reinterpret_cast<const float*>(p.packed);
 
+  // ring_mode 1: no block barrier per slot -- every warp ARRIVES on the slot's `empty` mbarrier when it is done with
+  // it and runs on; thread 0 re-arms the slot two iterations later (it only waits if a warp lags two slots behind)
+  uint64_t* empty = bars + kMaxStages;
+  const bool free_ring = p.ring_mode == 1 && p.nstage >= 3;
   if (tid == 0) {
-    for (int s = 0; s < p.nstage; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < p.nstage; ++s) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&empty[s], BT / kWarp);
+    }
     fence_mbar_init();
   }
   const float* th = reinterpret_cast<const float*>(p.theta) + (size_t)(c0 + (chain_ok ? tid : 0)) * p.D;
@@ -290,6 +297,13 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
 
   for (int it = 0; it < n_it; ++it) {
     const int s = it % p.nstage;
+    if (free_ring && tid == 0 && it >= 2 && it - 2 + p.nstage < n_it) {
+      const int ps = (it - 2) % p.nstage;
+      mbar_wait(&empty[ps], (uint32_t)(((it - 2) / p.nstage) & 1));
+      mbar_expect_tx(&bars[ps], tile_bytes);
+      tma_load_bulk(stage0 + (size_t)ps * tile_elems, packed + (size_t)(bt_begin + it - 2 + p.nstage) * tile_elems,
+                    tile_bytes, &bars[ps]);
+    }
     mbar_wait(&bars[s], (uint32_t)((it / p.nstage) & 1));
     const float* tile = stage0 + (size_t)s * tile_elems;
     const int64_t unit0 = (bt_begin + it) * TS;
@@ -409,6 +423,11 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
     for (int i = 1; i <= KB + 1; ++i) g64[(size_t)i * BT] += (double)acc[i];
 #pragma unroll
     for (int i = 2 + KB; i < NQ; ++i) g64[(size_t)i * BT] += (double)acc[i] * -kLn2D;  // covariate slots carry -log2(e)
+    if (free_ring) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+      continue;
+    }
     __syncthreads();
     if (tid == 0 && it + p.nstage < n_it) {
       mbar_expect_tx(&bars[s], tile_bytes);

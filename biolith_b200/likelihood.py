@@ -193,6 +193,14 @@ class OccupancyLikelihood:
         """Asynchronous evaluation on device pointers (what a jax.ffi custom call does)."""
         check(self._lib.bl_eval(self._h, theta_ptr, n_chains, logp_ptr, grad_ptr, stream), "bl_eval")
 
+    def plan(self, n_chains: int) -> dict:
+        """Which kernel evaluates a batch of ``n_chains`` chains and with what launch geometry (diagnostics / tests):
+        ``kernel`` 0 = site-parallel engine, 5 = K1d, 6 = K2d, 7 = K1s (small batches), 1-4 = round-1 chain kernels."""
+        k, gx, gy, bt = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(self._lib.bl_plan_kernel(self._h, int(n_chains), C.byref(k), C.byref(gx), C.byref(gy), C.byref(bt)),
+              "bl_plan_kernel")
+        return dict(kernel=k.value, grid=(gx.value, gy.value), block_threads=bt.value)
+
     def eval_timed(self, theta_ptr, n_chains, logp_ptr, grad_ptr, stream=0, iters=10) -> float:
         ms = C.c_float()
         check(self._lib.bl_eval_timed(self._h, theta_ptr, n_chains, logp_ptr, grad_ptr, stream, iters,
