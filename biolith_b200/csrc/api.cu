@@ -61,8 +61,8 @@ cudaError_t launch_repack_signed(const void* packed, void* out, const Layout& L,
 cudaError_t launch_occu_signed(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 bool occu_small_supported(int dtype, int ks, int ko, uint32_t flags);
 int occu_small_max_chains();
-int occu_small_block_threads(int CB);
-size_t occu_small_smem(const Layout& L, int nstage, int CB);
+int occu_small_block_threads(const Layout& L, int CB, size_t smem_budget);
+size_t occu_small_smem(const Layout& L, int nstage, int block_threads);
 cudaError_t launch_occu_small(const EvalParams& p, dim3 grid, size_t smem, cudaStream_t st, int* occ);
 bool occu_rn2_supported(int dtype, int ks, int ko, int J, int K, uint32_t flags);
 size_t occu_rn2_bytes(const Layout& L);
@@ -208,14 +208,15 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       pl.chain_variant = 0;
       pl.g.n_chunks = (C + ncmax - 1) / ncmax;
       pl.g.CB = (C + pl.g.n_chunks - 1) / pl.g.n_chunks;
-      pl.chain_bt = occu_small_block_threads(pl.g.CB);  // one block per SM, one TMA ring per warp
-      pl.g.WS = pl.chain_bt / kWarp; pl.g.WC = 1;
-      pl.g.n_block_tiles = (ds->L.n_tiles + pl.g.WS - 1) / pl.g.WS;
-      pl.g.nstage = kMaxStages;
       const size_t budget = ds->smem_limit - 24 * 1024;  // static shared memory + reserve
-      while (pl.g.nstage > 2 && occu_small_smem(ds->L, pl.g.nstage, pl.g.CB) > budget) --pl.g.nstage;
-      pl.g.smem_bytes = occu_small_smem(ds->L, pl.g.nstage, pl.g.CB);
-      if (pl.g.smem_bytes > budget) {  // very wide units: the engine
+      pl.chain_bt = occu_small_block_threads(ds->L, pl.g.CB, budget);  // one block per SM, one TMA ring per warp
+      if (pl.chain_bt > 0) {
+        pl.g.WS = pl.chain_bt / kWarp; pl.g.WC = 1;
+        pl.g.n_block_tiles = (ds->L.n_tiles + pl.g.WS - 1) / pl.g.WS;
+        pl.g.nstage = kMaxStages;
+        while (pl.g.nstage > 2 && occu_small_smem(ds->L, pl.g.nstage, pl.chain_bt) > budget) --pl.g.nstage;
+        pl.g.smem_bytes = occu_small_smem(ds->L, pl.g.nstage, pl.chain_bt);
+      } else {  // very wide units: the engine
         pl.chain_kernel = 0;
         pl.g = plan_geometry(ds->L, elem, C, ds->D, ds->DS, ds->num_sms, 2, ds->smem_limit, 0);
       }

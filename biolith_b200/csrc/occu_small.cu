@@ -153,7 +153,8 @@ __device__ __forceinline__ void small_decode(const float* __restrict__ tile, int
 // visits are decoded per chain from shared memory in quads (any J).
 template <int KS, int KO, bool J8, int NC>
 __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalParams p) {
-  constexpr int kSmallBT = small_bt(NC), kSmallWarps = kSmallBT / kWarp;
+  constexpr int kSmallBT = small_bt(NC), kSmallWarpsMax = kSmallBT / kWarp;
+  const int kSmallWarps = (int)blockDim.x / kWarp;  // fewer than the maximum when a warp-tile is wide (ring budget)
   constexpr int KSM = KS < 0 ? kSmallMaxKs : KS;
   constexpr int KBM = KSM + 1, KA = KO + 1, NG = KBM + KA;  // gradient slots in this kernel's (padded) order
   static_assert(NG <= 16 && KBM + KA <= kSmallThetaStride, "one 16-wide butterfly / theta row");
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
   float* stage0 = reinterpret_cast<float*>(smem_raw + kSmallHeader);
   __shared__ int s_is_last;
   __shared__ __align__(16) float s_th[NC * kSmallThetaStride];
-  __shared__ double s_red[kSmallWarps][NC][1 + 16];
+  __shared__ double s_red[kSmallWarpsMax][NC][1 + 16];
   __shared__ double s_scr[kSmallBT];  // scratch of the cooperative last-block reduction
   // one TMA ring PER WARP (warp-tile = 32 sites = F x 128 B, one cp.async.bulk each): no block barrier in the loop,
   // the warps drift freely (measured with a block-wide ring and one barrier per 4 warp-tiles: barrier stalls 0.65
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
   const int64_t wt_mine = wt_end - wt_begin - warp;  // this warp takes wt_begin + warp, + kSmallWarps, ...
   const int n_it = wt_mine > 0 ? (int)((wt_mine + kSmallWarps - 1) / kSmallWarps) : 0;
   const float* packed = reinterpret_cast<const float*>(p.packed) + (size_t)(wt_begin + warp) * tile_elems;
-  constexpr size_t kStep = kSmallWarps;  // warp-tiles between two iterations of a warp
+  const size_t kStep = (size_t)kSmallWarps;  // warp-tiles between two iterations of a warp
   uint64_t* wbars = bars + warp * kMaxStages;
   float* wstage0 = stage0 + (size_t)warp * p.nstage * tile_elems;
 
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
       tma_load_bulk(wstage0, packed, tile_bytes, &wbars[0]);
     }
   }
-  for (int i = tid; i < NC * kSmallThetaStride; i += kSmallBT) {
+  for (int i = tid; i < NC * kSmallThetaStride; i += (int)blockDim.x) {
     const int c = i / kSmallThetaStride, e = i % kSmallThetaStride;
     float v = 0.f;
     if (c < ncb) {
@@ -353,12 +354,11 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
   }
   __syncthreads();
   double* my_partial = p.partial + ((size_t)blockIdx.x * p.C + c0) * NQ;
-  for (int i = tid; i < ncb * NQ; i += kSmallBT) {
+  for (int i = tid; i < ncb * NQ; i += (int)blockDim.x) {
     const int c = i / NQ, q = i % NQ;
     // output order [logp | beta_0..ks | alpha_0..ko] from this kernel's padded slots [beta (KBM) | alpha (KA)]
     const int slot = q == 0 ? 0 : (q - 1 <= ks ? q : 1 + KBM + (q - 1 - (ks + 1)));
     double v = 0.0;
-#pragma unroll
     for (int w = 0; w < kSmallWarps; ++w) v += s_red[w][c][slot];
     my_partial[i] = v;
   }
@@ -383,10 +383,16 @@ bool occu_small_supported(int dtype, int ks, int ko, uint32_t flags) {
 }
 
 int occu_small_max_chains() { return kSmallMaxNC; }
-int occu_small_block_threads(int CB) { return small_bt(CB); }
+size_t occu_small_smem(const Layout& L, int nstage, int block_threads) {
+  return kSmallHeader + (size_t)nstage * (block_threads / kWarp) * L.F * kWarp * sizeof(float);
+}
 
-size_t occu_small_smem(const Layout& L, int nstage, int CB) {
-  return kSmallHeader + (size_t)nstage * (small_bt(CB) / kWarp) * L.F * kWarp * sizeof(float);
+// threads per block: as many warps as the register file carries for CB chains, fewer when the units are wide (every
+// warp owns a ring of >= 2 warp-tiles of F x 128 B); 0 = does not fit (the engine serves the shape)
+int occu_small_block_threads(const Layout& L, int CB, size_t smem_budget) {
+  int bt = small_bt(CB);
+  while (bt >= 128 && occu_small_smem(L, 2, bt) > smem_budget) bt -= 32;
+  return bt >= 128 ? bt : 0;
 }
 
 template <int KS, int KO, bool J8, int NC>
@@ -398,8 +404,8 @@ static cudaError_t launch_small_one(const EvalParams& p, dim3 grid, size_t smem,
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, small_bt(NC), smem);
-  kern<<<grid, small_bt(NC), smem, st>>>(p);
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, p.chain_bt, smem);
+  kern<<<grid, p.chain_bt, smem, st>>>(p);
   return cudaGetLastError();
 }
 
