@@ -261,73 +261,72 @@ __global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalP
 
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      if (c < ncb) {
-        float tt[kSmallThetaStride];
+      // rows c >= ncb of a ragged last chunk hold theta = 0: evaluated like any chain (finite), never published
+      float tt[kSmallThetaStride];
 #pragma unroll
-        for (int i = 0; i < kSmallThetaStride / 4; ++i) {
-          const float4 t = *reinterpret_cast<const float4*>(s_th + c * kSmallThetaStride + 4 * i);
-          tt[4 * i] = t.x; tt[4 * i + 1] = t.y; tt[4 * i + 2] = t.z; tt[4 * i + 3] = t.w;
-        }
-        float al[KA];
-#pragma unroll
-        for (int k = 0; k < KA; ++k) al[k] = tt[KBM + k];
-        float lgsum = 0.f, mx = 0.f, ga[KA];
-#pragma unroll
-        for (int k = 0; k < KA; ++k) ga[k] = 0.f;
-        if constexpr (J8) {
-          small_visits<KO, 8>(s8, sw8, al, lgsum, mx, ga);
-        } else {
-          uint32_t yw = yw0, mw = mw0;
-          for (int q = 0; q < nq; ++q) {
-            if (q > 0 && (q & 7) == 0) {
-              yw = __float_as_uint(tile[(off_y + (q >> 3)) * kWarp + lane]);
-              mw = __float_as_uint(tile[(off_m + (q >> 3)) * kWarp + lane]);
-            }
-            float s4[4], sw4[4][KO];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) small_decode<KO>(tile, lane, off_w, yw, mw, q * 4 + jj, J, s4[jj], sw4[jj]);
-            small_visits<KO, 4>(s4, sw4, al, lgsum, mx, ga);
-          }
-        }
-        float L1 = -sfu::kLn2 * (lgsum - cnt);
-        const bool slow = mx >= kSmClampProduct;
-        if (__any_sync(0xffffffffu, slow)) {
-          const SmallSlow<KO> so = small_slow_site<KO>(tile, lane, off_w, off_y, off_m, J, s_th + c * kSmallThetaStride + KBM);
-          if (slow) {
-            L1 = so.L1;
-#pragma unroll
-            for (int k = 0; k < KA; ++k) ga[k] = so.ga[k];
-          }
-        }
-        float eta = tt[0];
-#pragma unroll
-        for (int k = 0; k < KSM; ++k) eta = fmaf(x[k], tt[1 + k], eta);
-        // site level as in K1d: psi~ = sigmoid(xc), a = log psi~ + L1, b = log(1 - psi~) + n1 log tiny,
-        //   d = a - b = xc + L1 - n1 log tiny,  logaddexp(a, b) = max(al, bl) - max(xc, 0) + log(u_d / u_e)
-        const float xc = fminf(fmaxf(eta, sfu::kXLo), sfu::kXHi);
-        const bool inr = xc == eta;
-        const float te = sm_exp_neg_abs(xc);
-        const float ue = 1.0f + te;
-        float inve = sfu::rcp(ue);
-        inve = fmaf(inve, fmaf(-ue, inve, 1.0f), inve);
-        const float psi = (xc >= 0.f) ? inve : te * inve;
-        const float av = xc + L1;
-        const float d = av - bl0;
-        const float td = sm_exp_neg_abs(d);
-        const float ud = 1.0f + td;
-        float invd = sfu::rcp(ud);
-        invd = fmaf(invd, fmaf(-ud, invd, 1.0f), invd);
-        const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
-        const float r = rr * vf;
-        const float ell = fmaf(sfu::lg2(ud * inve), sfu::kLn2, (d >= 0.f ? av : bl0) - fmaxf(xc, 0.f)) * vf;
-        const float geta = inr ? (rr - psi) * vf : 0.f;
-        lp64[c] += (double)ell;
-        acc[c][0] += geta;
-#pragma unroll
-        for (int k = 0; k < KSM; ++k) acc[c][1 + k] = fmaf(geta, x[k], acc[c][1 + k]);
-#pragma unroll
-        for (int k = 0; k < KA; ++k) acc[c][KBM + k] = fmaf(r, ga[k], acc[c][KBM + k]);
+      for (int i = 0; i < kSmallThetaStride / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(s_th + c * kSmallThetaStride + 4 * i);
+        tt[4 * i] = t.x; tt[4 * i + 1] = t.y; tt[4 * i + 2] = t.z; tt[4 * i + 3] = t.w;
       }
+      float al[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) al[k] = tt[KBM + k];
+      float lgsum = 0.f, mx = 0.f, ga[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) ga[k] = 0.f;
+      if constexpr (J8) {
+        small_visits<KO, 8>(s8, sw8, al, lgsum, mx, ga);
+      } else {
+        uint32_t yw = yw0, mw = mw0;
+        for (int q = 0; q < nq; ++q) {
+          if (q > 0 && (q & 7) == 0) {
+            yw = __float_as_uint(tile[(off_y + (q >> 3)) * kWarp + lane]);
+            mw = __float_as_uint(tile[(off_m + (q >> 3)) * kWarp + lane]);
+          }
+          float s4[4], sw4[4][KO];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) small_decode<KO>(tile, lane, off_w, yw, mw, q * 4 + jj, J, s4[jj], sw4[jj]);
+          small_visits<KO, 4>(s4, sw4, al, lgsum, mx, ga);
+        }
+      }
+      float L1 = -sfu::kLn2 * (lgsum - cnt);
+      const bool slow = mx >= kSmClampProduct;
+      if (__any_sync(0xffffffffu, slow)) {
+        const SmallSlow<KO> so = small_slow_site<KO>(tile, lane, off_w, off_y, off_m, J, s_th + c * kSmallThetaStride + KBM);
+        if (slow) {
+          L1 = so.L1;
+#pragma unroll
+          for (int k = 0; k < KA; ++k) ga[k] = so.ga[k];
+        }
+      }
+      float eta = tt[0];
+#pragma unroll
+      for (int k = 0; k < KSM; ++k) eta = fmaf(x[k], tt[1 + k], eta);
+      // site level as in K1d: psi~ = sigmoid(xc), a = log psi~ + L1, b = log(1 - psi~) + n1 log tiny,
+      //   d = a - b = xc + L1 - n1 log tiny,  logaddexp(a, b) = max(al, bl) - max(xc, 0) + log(u_d / u_e)
+      const float xc = fminf(fmaxf(eta, sfu::kXLo), sfu::kXHi);
+      const bool inr = xc == eta;
+      const float te = sm_exp_neg_abs(xc);
+      const float ue = 1.0f + te;
+      float inve = sfu::rcp(ue);
+      inve = fmaf(inve, fmaf(-ue, inve, 1.0f), inve);
+      const float psi = (xc >= 0.f) ? inve : te * inve;
+      const float av = xc + L1;
+      const float d = av - bl0;
+      const float td = sm_exp_neg_abs(d);
+      const float ud = 1.0f + td;
+      float invd = sfu::rcp(ud);
+      invd = fmaf(invd, fmaf(-ud, invd, 1.0f), invd);
+      const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
+      const float r = rr * vf;
+      const float ell = fmaf(sfu::lg2(ud * inve), sfu::kLn2, (d >= 0.f ? av : bl0) - fmaxf(xc, 0.f)) * vf;
+      const float geta = inr ? (rr - psi) * vf : 0.f;
+      lp64[c] += (double)ell;
+      acc[c][0] += geta;
+#pragma unroll
+      for (int k = 0; k < KSM; ++k) acc[c][1 + k] = fmaf(geta, x[k], acc[c][1 + k]);
+#pragma unroll
+      for (int k = 0; k < KA; ++k) acc[c][KBM + k] = fmaf(r, ga[k], acc[c][KBM + k]);
     }
     __syncwarp();  // every lane is done reading stage st
     if (lane == 0 && it + p.nstage < n_it) {
