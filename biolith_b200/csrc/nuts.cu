@@ -16,6 +16,7 @@
 // numpyro's threefry streams.  Energies and the tree weights are fp64 (a 1M-site log-density is
 // ~1e6 in magnitude: fp32 would leave delta-energy a resolution of 0.5).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -107,14 +108,23 @@ struct Philox {
   }
 };
 
+// The state of chain c: element e of a field lives at base[e * stride].  Global view: base = buffer + c, stride = C
+// (coalesced across chains); staged view (nuts_advance_staged_kernel): the chain's state copied to shared memory,
+// stride = 1.
 struct ChainView {
   const NutsParams& p;
   int c;
-  __device__ double& v(int f, int d) const { return p.vec[((size_t)f * p.D + d) * p.C + c]; }
-  __device__ double& s(int f) const { return p.sc[(size_t)f * p.C + c]; }
-  __device__ int& i(int f) const { return p.isc[(size_t)f * p.C + c]; }
+  double* vec; double* sc; int* isc; double* ckpt;
+  size_t stride;
+  __device__ ChainView(const NutsParams& p_, int c_)
+      : p(p_), c(c_), vec(p_.vec + c_), sc(p_.sc + c_), isc(p_.isc + c_), ckpt(p_.ckpt + c_), stride((size_t)p_.C) {}
+  __device__ ChainView(const NutsParams& p_, int c_, double* vec_, double* sc_, int* isc_, double* ckpt_)
+      : p(p_), c(c_), vec(vec_), sc(sc_), isc(isc_), ckpt(ckpt_), stride(1) {}
+  __device__ double& v(int f, int d) const { return vec[((size_t)f * p.D + d) * stride]; }
+  __device__ double& s(int f) const { return sc[(size_t)f * stride]; }
+  __device__ int& i(int f) const { return isc[(size_t)f * stride]; }
   __device__ double& ck(int which, int level, int d) const {
-    return p.ckpt[(((size_t)which * p.max_depth + level) * p.D + d) * p.C + c];
+    return ckpt[(((size_t)which * p.max_depth + level) * p.D + d) * stride];
   }
   __device__ void copy(int dst, int src) const {
     for (int d = 0; d < p.D; ++d) v(dst, d) = v(src, d);
@@ -286,7 +296,7 @@ template <typename T>
 __global__ void nuts_start_kernel(NutsParams p) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
-  ChainView cv{p, c};
+  ChainView cv(p, c);
   p.slot[c] = c;
   Philox rng{(unsigned int)p.seed, (unsigned int)(p.seed >> 32), (unsigned int)c, 0x6e757473u, 0ull};
   const T* th = reinterpret_cast<const T*>(p.theta) + (size_t)c * p.D;
@@ -316,11 +326,10 @@ __global__ void nuts_start_kernel(NutsParams p) {
   cv.i(I_CTR_HI) = (int)(unsigned int)(rng.ctr >> 32);
 }
 
+// One transition step of chain cv.c: consumes the (logp, grad) leaf of its pending position.
 template <typename T>
-__global__ void nuts_advance_kernel(NutsParams p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.C) return;
-  ChainView cv{p, c};
+__device__ void nuts_advance_chain(const NutsParams& p, const ChainView& cv) {
+  const int c = cv.c;
   if (cv.i(I_DONE)) return;
   const int D = p.D;
   Philox rng{(unsigned int)p.seed, (unsigned int)(p.seed >> 32), (unsigned int)c, 0x6e757473u,
@@ -497,6 +506,57 @@ __global__ void nuts_advance_kernel(NutsParams p) {
   set_next_leaf<T>(cv);
   cv.i(I_CTR_LO) = (int)(unsigned int)rng.ctr;
   cv.i(I_CTR_HI) = (int)(unsigned int)(rng.ctr >> 32);
+}
+
+template <typename T>
+__global__ void nuts_advance_kernel(NutsParams p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  nuts_advance_chain<T>(p, ChainView(p, c));
+}
+
+// Few chains (what `fit` with the reference's default num_chains = 5 runs, biolith/utils/fit.py:24): thread-per-chain
+// walks ~300 dependent global-memory accesses per step (measured: ~45 us per leapfrog at 5 chains, 40 % of the step
+// beside a 63 us evaluation).  Here ONE WARP per chain copies the chain's state (~(27 D + 2 depth D) doubles) into
+// shared memory with all its lanes (independent loads, one or two round trips), lane 0 runs the SAME transition code
+// on the shared-memory view, and the warp writes the state back.  Same arithmetic in the same order as
+// nuts_advance_kernel: the draws are bit-identical.
+constexpr int kStagedWarps = 4;
+
+__host__ __device__ inline size_t nuts_staged_doubles(int D, int max_depth) {
+  return (size_t)V_COUNT * D + S_COUNT + 2 * (size_t)max_depth * D;
+}
+__host__ __device__ inline size_t nuts_staged_bytes_per_chain(int D, int max_depth) {
+  return nuts_staged_doubles(D, max_depth) * sizeof(double) + ((I_COUNT * sizeof(int) + 7) & ~size_t(7));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStagedWarps * 32) nuts_advance_staged_kernel(NutsParams p) {
+  extern __shared__ __align__(16) unsigned char nuts_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * kStagedWarps + warp;
+  if (c >= p.C) return;
+  if (p.isc[(size_t)I_DONE * p.C + c]) return;  // warp-uniform
+  const int D = p.D;
+  unsigned char* base = nuts_smem + (size_t)warp * nuts_staged_bytes_per_chain(D, p.max_depth);
+  double* s_vec = reinterpret_cast<double*>(base);
+  double* s_sc = s_vec + (size_t)V_COUNT * D;
+  double* s_ck = s_sc + S_COUNT;
+  int* s_i = reinterpret_cast<int*>(s_ck + 2 * (size_t)p.max_depth * D);
+  const int nv = V_COUNT * D, nc = 2 * p.max_depth * D;
+  const size_t C = (size_t)p.C;
+  for (int e = lane; e < nv; e += 32) s_vec[e] = p.vec[(size_t)e * C + c];
+  for (int e = lane; e < nc; e += 32) s_ck[e] = p.ckpt[(size_t)e * C + c];
+  if (lane < S_COUNT) s_sc[lane] = p.sc[(size_t)lane * C + c];
+  if (lane < I_COUNT) s_i[lane] = p.isc[(size_t)lane * C + c];
+  static_assert(S_COUNT <= 32 && I_COUNT <= 32, "one lane per scalar field");
+  __syncwarp();
+  if (lane == 0) nuts_advance_chain<T>(p, ChainView(p, c, s_vec, s_sc, s_i, s_ck));
+  __syncwarp();
+  for (int e = lane; e < nv; e += 32) p.vec[(size_t)e * C + c] = s_vec[e];
+  for (int e = lane; e < nc; e += 32) p.ckpt[(size_t)e * C + c] = s_ck[e];
+  if (lane < S_COUNT) p.sc[(size_t)lane * C + c] = s_sc[lane];
+  if (lane < I_COUNT) p.isc[(size_t)lane * C + c] = s_i[lane];
 }
 
 // Re-number the rows of the evaluation batch so that the still-running chains are contiguous (one
@@ -681,10 +741,25 @@ int bl_nuts_run(bl_nuts* s, int64_t max_steps, int32_t poll_every, int64_t* step
     g_launches.fetch_add(1);
     s->started = true;
   }
+  // few chains and a state that fits in shared memory: one warp per chain (see nuts_advance_staged_kernel)
+  const size_t staged_smem = (size_t)kStagedWarps * nuts_staged_bytes_per_chain(p.D, p.max_depth);
+  bool staged = p.C <= 64 && staged_smem <= 96 * 1024;
+  if (const char* ev = getenv("BL_NUTS_STAGED")) staged = staged && atoi(ev) != 0;
+  if (staged && staged_smem > 48 * 1024) {
+    cudaError_t ce = f32 ? cudaFuncSetAttribute(nuts_advance_staged_kernel<float>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem)
+                         : cudaFuncSetAttribute(nuts_advance_staged_kernel<double>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem);
+    if (ce != cudaSuccess) { cudaGetLastError(); staged = false; }
+  }
+  const int sblocks = (p.C + kStagedWarps - 1) / kStagedWarps;
   auto one_step = [&]() -> int {
     int rc = eval_device(ds, p.theta, s->n_rows, s->d_logp_t, s->d_grad, s->stream, 0, s->d_logp64);
     if (rc) return rc;
-    if (f32) nuts_advance_kernel<float><<<blocks, threads, 0, s->stream>>>(p);
+    if (staged) {
+      if (f32) nuts_advance_staged_kernel<float><<<sblocks, kStagedWarps * 32, staged_smem, s->stream>>>(p);
+      else nuts_advance_staged_kernel<double><<<sblocks, kStagedWarps * 32, staged_smem, s->stream>>>(p);
+    } else if (f32) nuts_advance_kernel<float><<<blocks, threads, 0, s->stream>>>(p);
     else nuts_advance_kernel<double><<<blocks, threads, 0, s->stream>>>(p);
     g_launches.fetch_add(1);
     return BL_OK;

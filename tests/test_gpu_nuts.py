@@ -192,3 +192,28 @@ def test_fit_occu_cs_recovers_truth():
     assert np.all(s["beta"]["r_hat"] < 1.05) and np.all(s["sigma1"]["r_hat"] < 1.05)
     ss = res.mcmc.info["site_summary"]
     assert np.corrcoef(ss["occupancy_prob"][:, 0], true["z"][0, 0, :])[0, 1] > 0.9
+
+
+@pytest.mark.parametrize("model,chains", [("occu", 5), ("occu_rn", 3)])
+def test_staged_transition_kernel_is_bit_identical(monkeypatch, model, chains):
+    """Few chains run the NUTS transition with one warp per chain on a shared-memory copy of the chain's state
+    (nuts_advance_staged_kernel); it executes the same arithmetic in the same order as the thread-per-chain kernel,
+    so with the same seed every draw, statistic and adapted step size must be identical."""
+    import biolith_b200 as bb
+
+    name = "occu_5x3" if model == "occu" else "rn_5x3"
+    g = load_golden(name)
+    d = g["data"]
+    out = {}
+    for staged in ("1", "0"):
+        monkeypatch.setenv("BL_NUTS_STAGED", staged)
+        kw = dict(max_abundance=g["model_kwargs"].get("max_abundance", 100)) if model == "occu_rn" else {}
+        with bb.OccupancyLikelihood(model, d["site_covs"], d["obs_covs"], d["obs"], max_chains=chains, **kw) as lk:
+            s = bb.NutsSampler(lk, chains, 150, 100, seed=11)
+            assert s.run(timeout=300)
+            out[staged] = s.results()
+            s.close()
+    a, b = out["1"], out["0"]
+    assert np.all(a["n_saved"] == 100)
+    for k in ("samples", "accept_prob", "num_steps", "diverging", "step_size", "leapfrogs"):
+        assert np.array_equal(a[k], b[k]), f"{k} differs between the staged and the thread-per-chain transition kernel"
