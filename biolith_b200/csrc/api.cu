@@ -184,8 +184,9 @@ static int plan_for(bl_dataset* ds, int C, Plan** out) {
       pl.chain_kernel = 1;
     if (pl.chain_kernel == 1 && ds->packed_signed) {  // K1d unless the tuning switch asks for K1c
       const char* ev = getenv("BL_OCCU_CHAIN_KERNEL");
-      if (!ev || atoi(ev) != 1) pl.chain_kernel = 5;
+      if (!ev || atoi(ev) != 1 || ds->strict_chain) pl.chain_kernel = 5;
     }
+    if (pl.chain_kernel == 1 && ds->strict_chain) pl.chain_kernel = 0;  // K1c has no libm form
     if (want_chain && ds->desc.model == BL_MODEL_OCCU_RN &&
         occu_rn_chain_supported(ds->desc.dtype, ds->L.ks, ds->L.ko, ds->desc.flags) &&
         occu_rn_chain_smem(ds->L, 2, ds->desc.max_abundance, ds->D, occu_rn_chain_block_threads(C)) <= ds->smem_limit)
@@ -515,8 +516,11 @@ int bl_dataset_create(const bl_desc* d, const void* y, const void* X, const void
   bl_dataset* ds = new (std::nothrow) bl_dataset();
   if (!ds) return fail(BL_ERR_NOMEM, "host allocation failed");
   ds->desc = *d;
-  ds->force_engine = (d->flags & BL_FLAG_STRICT_MATH) != 0;
   ds->L = make_layout(d->model, d->n_sites, d->n_periods, d->n_replicates, d->n_site_covs, d->n_obs_covs);
+  // strict math: the libm-accurate engine, except for occu shapes K1d covers (its STRICT instantiations)
+  ds->strict_chain = (d->flags & BL_FLAG_STRICT_MATH) && d->model == BL_MODEL_OCCU && !re && d->n_species <= 1 &&
+                     occu_signed_supported(d->dtype, d->n_site_covs, d->n_obs_covs, d->flags);
+  ds->force_engine = (d->flags & BL_FLAG_STRICT_MATH) != 0 && !ds->strict_chain;
   ds->n_extras = d->model == BL_MODEL_OCCU_CS ? 4 : (fpc ? 1 : 0) + (fpu ? 1 : 0);
   ds->D = d->n_site_covs + 1 + d->n_obs_covs + 1 + ds->n_extras;
   int derived = d->model == BL_MODEL_OCCU ? occu_derived_slots(d->flags)

@@ -51,7 +51,8 @@ struct bl_dataset {
   double* ms_lp64 = nullptr;
   int ms_cap = 0;
   bool re = false;            // occu with site / observation random effects (occu_re.cu): its own kernel and layout
-  bool force_engine = false;  // BL_FLAG_STRICT_MATH: always use the site-parallel libm-accurate engine
+  bool force_engine = false;  // BL_FLAG_STRICT_MATH (shapes K1d does not cover), random effects: the site-parallel engine
+  bool strict_chain = false;  // BL_FLAG_STRICT_MATH on an occu shape K1d covers: its libm instantiations for C >= 32
   // bl_eval_host staging
   void *d_theta = nullptr, *d_out = nullptr, *h_theta = nullptr, *h_out = nullptr;
   int host_cap = 0;

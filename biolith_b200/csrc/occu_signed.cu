@@ -41,10 +41,32 @@ constexpr double kLog2eD = 1.4426950408889634074, kLn2D = 0.6931471805599453094;
 constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - (float)log2(e): second term of the two-float constant
 constexpr float kLn2Lo = -1.9046542121259336e-09f;  // ln(2)   - (float)ln(2)
 
+// Elementary functions of K1d.  Default: the bounded-error SFU forms (ex2.approx, lg2.approx, rcp.approx + Newton).
+// STRICT (BL_FLAG_STRICT_MATH): libm exp2f / log2f and IEEE division -- north_star's "fast-math-free" clause -- in the
+// SAME formulation (one exponential per visit, product-log, batch inversion are algebra, not approximations), so the
+// conformant path costs ~100 instructions per (site, chain) more instead of running the 4 x slower engine.
+template <bool STRICT> struct SMath {
+  static __device__ __forceinline__ float ex2(float x) {
+    if constexpr (STRICT) return exp2f(x); else return sfu::ex2(x);
+  }
+  static __device__ __forceinline__ float lg2(float x) {
+    if constexpr (STRICT) return log2f(x); else return sfu::lg2(x);
+  }
+  static __device__ __forceinline__ float inv(float x) {
+    if constexpr (STRICT) {
+      return 1.0f / x;
+    } else {
+      const float r = sfu::rcp(x);
+      return fmaf(r, fmaf(-x, r, 1.0f), r);  // Newton: MUFU.RCP's bias would add up over 10^7 visits
+    }
+  }
+};
+
 // 2^(t log2 e) with the two-float constant: the argument carries no fixed relative error
+template <bool STRICT>
 __device__ __forceinline__ float exp_neg_abs(float x) {
   const float t = -fabsf(x);
-  return sfu::ex2(fmaf(t, kLog2eLo, t * sfu::kLog2e));
+  return SMath<STRICT>::ex2(fmaf(t, kLog2eLo, t * sfu::kLog2e));
 }
 
 
@@ -130,7 +152,7 @@ size_t occu_signed_bytes(const Layout& L) {
 // ---- exact per-visit form for lanes with a clamped visit (rare): K1c's arithmetic on the signed record ----------
 template <int KO> struct SlowOut { float L1; float ga[KO + 1]; };
 
-template <int KO>
+template <int KO, bool STRICT>
 __device__ __noinline__ SlowOut<KO> slow_visits(const float* __restrict__ vis, int nvis,
                                                const float* __restrict__ alpha) {
   constexpr int VR = KO + 1 <= 2 ? 2 : (KO + 1 <= 4 ? 4 : 8);
@@ -148,9 +170,16 @@ __device__ __noinline__ SlowOut<KO> slow_visits(const float* __restrict__ vis, i
     const float xp = fmaf(sgn, alpha[0], -fmaf(x2, kLn2Lo, x2 * sfu::kLn2));  // x' = sgn (alpha0 + W . alpha)
     const float x = sgn * xp;
     const float yf = sgn > 0.f ? 1.f : 0.f;
-    const sfu::SoftSig ss = sfu::softsig<true>(x);
-    o.L1 += fmaf(yf, ss.xc, -ss.s);
-    const float g = ss.inr ? (yf - ss.p) : 0.f;
+    float g;
+    if constexpr (STRICT) {  // the engine's libm form (common.cuh log_sigmoid_pair)
+      const LogSig<float> ls = log_sigmoid_pair<float>(x);
+      o.L1 += sgn > 0.f ? ls.lp : ls.l1mp;
+      g = ls.inr ? (sgn > 0.f ? ls.q : -ls.p) : 0.f;
+    } else {
+      const sfu::SoftSig ss = sfu::softsig<true>(x);
+      o.L1 += fmaf(yf, ss.xc, -ss.s);
+      g = ss.inr ? (yf - ss.p) : 0.f;
+    }
     const float gs = g * sgn;  // d/d alpha_k = g W_k; kept in the record's units: (g sgn) v_k = -log2(e) g W_k, k >= 1
 #pragma unroll
     for (int k = 0; k <= KO; ++k) o.ga[k] = fmaf(gs, v[k], o.ga[k]);
@@ -179,9 +208,10 @@ template <int N> struct LoadVec {
 // NV = 4 or 8 visits of one site: x2 = v . a2, e = 2^x2, u = 1 + e; ONE lg2 and ONE rcp (+ Newton) for the product of
 // all NV factors (batch inversion through the pair-product tree), q_j = e_j / u_j, ga += q_j v_j.  `mx` tracks the
 // largest pair product: while it stays below 2^23 no visit is clamped and the product of 8 factors is < 2^92.
-template <int KO, int NV>
+template <int KO, int NV, bool STRICT>
 __device__ __forceinline__ void visit_block(const float* __restrict__ vp, const float (&a2)[KO + 2], float& lgsum,
                                             float& mx, float (&ga)[KO + 1]) {
+  using M = SMath<STRICT>;
   constexpr int VR = KO + 1 <= 2 ? 2 : (KO + 1 <= 4 ? 4 : 8);
   static_assert(NV == 4 || NV == 8, "visits are processed in quads or octets");
   float v[NV * VR];
@@ -193,7 +223,7 @@ __device__ __forceinline__ void visit_block(const float* __restrict__ vp, const 
 #pragma unroll
     for (int k = 0; k < KO; ++k) x2 = fmaf(v[j * VR + 1 + k], a2[1 + k], x2);
     x2 = fmaf(v[j * VR], a2[0], x2);    // + sgn * A_hi
-    e[j] = sfu::ex2(x2);
+    e[j] = M::ex2(x2);
     u[j] = 1.0f + e[j];
   }
   float pr[NV / 2], rp[NV / 2];  // pair products and their reciprocals
@@ -202,17 +232,15 @@ __device__ __forceinline__ void visit_block(const float* __restrict__ vp, const 
   if constexpr (NV == 4) {
     const float pp = pr[0] * pr[1];
     mx = fmaxf(mx, fmaxf(pr[0], pr[1]));
-    float rinv = sfu::rcp(pp);
-    rinv = fmaf(rinv, fmaf(-pp, rinv, 1.0f), rinv);  // Newton: MUFU.RCP's bias would add up over 10^7 visits
-    lgsum += sfu::lg2(pp);
+    const float rinv = M::inv(pp);
+    lgsum += M::lg2(pp);
     rp[0] = rinv * pr[1];
     rp[1] = rinv * pr[0];
   } else {
     const float pa = pr[0] * pr[1], pb = pr[2] * pr[3], pp = pa * pb;
     mx = fmaxf(fmaxf(mx, fmaxf(pr[0], pr[1])), fmaxf(pr[2], pr[3]));
-    float rinv = sfu::rcp(pp);
-    rinv = fmaf(rinv, fmaf(-pp, rinv, 1.0f), rinv);
-    lgsum += sfu::lg2(pp);
+    const float rinv = M::inv(pp);
+    lgsum += M::lg2(pp);
     const float ra = rinv * pb, rb = rinv * pa;  // 1 / (u0 u1 u2 u3), 1 / (u4 u5 u6 u7)
     rp[0] = ra * pr[1]; rp[1] = ra * pr[0];
     rp[2] = rb * pr[3]; rp[3] = rb * pr[2];
@@ -229,8 +257,9 @@ __device__ __forceinline__ void visit_block(const float* __restrict__ vp, const 
 // Tried and rejected (measured, config 2): a dedicated producer warp with full / empty mbarrier pairs instead of
 // the block barrier per ring slot (288 threads -> 96..112 registers): 7.76 ms against 7.32 ms; three resident
 // blocks per SM (72..80 registers, spills): 8.2 ms.
-template <int KS, int KO, int NQD, int NS, int MINB, int BT>
+template <int KS, int KO, int NQD, int NS, int MINB, int BT, bool STRICT>
 __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams p, const SignedLayout S) {
+  using M = SMath<STRICT>;
   constexpr int KSM = KS < 0 ? kSignedMaxKs : KS;
   constexpr int KB = KSM + 1, KA = KO + 1, NQ = 1 + KB + KA;
   constexpr int VR = KO + 1 <= 2 ? 2 : (KO + 1 <= 4 ? 4 : 8);
@@ -324,18 +353,18 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
         if constexpr (NQD == 2) {  // 8 visits: one octet per site
 #pragma unroll
           for (int i = 0; i < NS; ++i)
-            visit_block<KO, 8>(rec + (size_t)i * R + XR + 4, a2, lgsum[i], mx[i], ga[i]);
+            visit_block<KO, 8, STRICT>(rec + (size_t)i * R + XR + 4, a2, lgsum[i], mx[i], ga[i]);
         } else {
           int q = 0;
           for (; q + 1 < nq; q += 2) {
 #pragma unroll
             for (int i = 0; i < NS; ++i)
-              visit_block<KO, 8>(rec + (size_t)i * R + XR + 4 + q * 4 * VR, a2, lgsum[i], mx[i], ga[i]);
+              visit_block<KO, 8, STRICT>(rec + (size_t)i * R + XR + 4 + q * 4 * VR, a2, lgsum[i], mx[i], ga[i]);
           }
           if (q < nq) {
 #pragma unroll
             for (int i = 0; i < NS; ++i)
-              visit_block<KO, 4>(rec + (size_t)i * R + XR + 4 + q * 4 * VR, a2, lgsum[i], mx[i], ga[i]);
+              visit_block<KO, 4, STRICT>(rec + (size_t)i * R + XR + 4 + q * 4 * VR, a2, lgsum[i], mx[i], ga[i]);
           }
         }
         float L1[NS], n1[NS], vf[NS];
@@ -350,7 +379,7 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
         if (__any_sync(0xffffffffu, slow)) {
 #pragma unroll
           for (int i = 0; i < NS; ++i) {
-            const SlowOut<KO> so = slow_visits<KO>(rec + (size_t)i * R + XR + 4, 4 * nq, th_alpha);
+            const SlowOut<KO> so = slow_visits<KO, STRICT>(rec + (size_t)i * R + XR + 4, 4 * nq, th_alpha);
             if (mx[i] >= kClampProduct) {
               L1[i] = so.L1;
 #pragma unroll
@@ -382,22 +411,20 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
           //   d = a - b = xc + L1 - n1 log tiny,   logaddexp(a, b) = max(d, 0) + n1 log tiny - max(xc, 0) + log(u_d / u_e)
           const float xc = fminf(fmaxf(eta[i], sfu::kXLo), sfu::kXHi);
           const bool inr = xc == eta[i];
-          const float te = exp_neg_abs(xc);
+          const float te = exp_neg_abs<STRICT>(xc);
           const float ue = 1.0f + te;
-          float inve = sfu::rcp(ue);
-          inve = fmaf(inve, fmaf(-ue, inve, 1.0f), inve);
+          const float inve = M::inv(ue);
           const float psi = (xc >= 0.f) ? inve : te * inve;
           const float bl = n1[i] * log_tiny;
           const float al = xc + L1[i];
           const float d = al - bl;
-          const float td = exp_neg_abs(d);
+          const float td = exp_neg_abs<STRICT>(d);
           const float ud = 1.0f + td;
-          float invd = sfu::rcp(ud);
-          invd = fmaf(invd, fmaf(-ud, invd, 1.0f), invd);
+          const float invd = M::inv(ud);
           const float rr = (d >= 0.f) ? invd : td * invd;  // P(z = 1 | y)
           const float r = rr * vf[i];
           // max(a, b) picked by select, not as b + max(d, 0): n1 log tiny ~ -87 n1 would cost the sum its low bits
-          const float ell = (fmaf(sfu::lg2(ud * inve), sfu::kLn2, (d >= 0.f ? al : bl) - fmaxf(xc, 0.f))) * vf[i];
+          const float ell = (fmaf(M::lg2(ud * inve), sfu::kLn2, (d >= 0.f ? al : bl) - fmaxf(xc, 0.f))) * vf[i];
           geta[i] = inr ? (rr - psi) * vf[i] : 0.f;
           logp64 += (double)ell;  // fp64 per unit: NUTS needs energy *differences* of a ~1e6-sized sum
           acc[1] += geta[i];
@@ -447,10 +474,10 @@ __global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams 
   finish_block<float>(p, c0, ncb, &s_is_last);
 }
 
-template <int KS, int KO, int NQD, int NS, int MINB, int BT>
+template <int KS, int KO, int NQD, int NS, int MINB, int BT, bool STRICT = false>
 static cudaError_t launch_signed_one(const EvalParams& p, const SignedLayout& S, dim3 grid, size_t smem,
                                      cudaStream_t st, int* occ) {
-  auto kern = occu_signed_kernel<KS, KO, NQD, NS, MINB, BT>;
+  auto kern = occu_signed_kernel<KS, KO, NQD, NS, MINB, BT, STRICT>;
   constexpr int NT = BT;
   static bool configured = false;
   if (!configured) {
@@ -463,8 +490,12 @@ static cudaError_t launch_signed_one(const EvalParams& p, const SignedLayout& S,
   return cudaGetLastError();
 }
 
+// BL_FLAG_STRICT_MATH is supported (the STRICT instantiations); BL_STRICT_ENGINE=1 sends it back to the engine (A/B)
 bool occu_signed_supported(int dtype, int ks, int ko, uint32_t flags) {
   if (dtype != BL_F32) return false;
+  if (flags & BL_FLAG_STRICT_MATH)
+    if (const char* e = getenv("BL_STRICT_ENGINE"))
+      if (atoi(e) != 0) return false;
   if (flags & (BL_FLAG_FP_CONSTANT | BL_FLAG_FP_UNOCCUPIED)) return false;
   return ks >= 0 && ks <= kSignedMaxKs && ko >= 1 && ko <= 4;
 }
@@ -496,6 +527,10 @@ template <int KS, int KO, int NQD>
 static cudaError_t launch_signed_bt(const EvalParams& p, const SignedLayout& S, dim3 grid, size_t smem,
                                     cudaStream_t st, int* occ) {
   const int ns = signed_ns();
+  if (p.flags & BL_FLAG_STRICT_MATH) {  // libm exp2f / log2f, IEEE division (the tuning variants are SFU-only)
+    if (p.chain_bt == 128) return launch_signed_one<KS, KO, NQD, 2, 4, 128, true>(p, S, grid, smem, st, occ);
+    return launch_signed_one<KS, KO, NQD, 2, 2, 256, true>(p, S, grid, smem, st, occ);
+  }
   if (p.chain_bt == 128) {
     if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 4, 128>(p, S, grid, smem, st, occ);
     return launch_signed_one<KS, KO, NQD, 2, 4, 128>(p, S, grid, smem, st, occ);

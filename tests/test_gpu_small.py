@@ -97,3 +97,30 @@ def test_small_kernel_matches_engine_and_repeats(monkeypatch):
         lp0, gr0 = lk.logp_and_grad(th)
     np.testing.assert_allclose(lp, lp0, rtol=1e-6)
     np.testing.assert_allclose(gr, gr0, rtol=1e-5, atol=1e-5 * np.abs(gr0).max())
+
+
+@pytest.mark.parametrize("ks,ko,J", [(5, 3, 8), (2, 2, 5), (8, 4, 13), (1, 1, 3)])
+def test_strict_math_runs_the_chain_kernel_with_libm(ks, ko, J):
+    """BL_FLAG_STRICT_MATH (north_star's "fast-math-free expf / log1pf") on occu with >= 32 chains: K1d's STRICT
+    instantiations (libm exp2f / log2f, IEEE division, the engine's libm clamp form in the fallback), not the 4 x
+    slower engine; same 1e-5 bar against the oracle, including thetas at the clamps."""
+    import biolith_b200 as bb
+    from oracle import occupancy as orc
+
+    rng = np.random.default_rng(31 * ks + J)
+    X, W, y = _data(rng, 3001, 1, J, ks, ko)
+    pr = orc.prepare(X, W, y)
+    D = ks + ko + 2
+    th = rng.uniform(-2, 2, size=(70, D))
+    th[1] *= 6.0
+    th[2] *= 15.0
+    th = th.astype(np.float32)
+    idx = [0, 1, 2, 33, 69]
+    ref_lp, ref_gr = orc.logp_grad("occu", th[idx].astype(np.float64), pr)
+    with bb.OccupancyLikelihood("occu", X, W, y, strict_math=True) as lk:
+        assert lk.plan(70)["kernel"] == 5 and lk.plan(5)["kernel"] == 0
+        lp, gr = lk.logp_and_grad(th)
+        assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"strict K1d ks={ks} ko={ko} J={J}")
+        lp5, gr5 = lk.logp_and_grad(th[:5])  # the libm engine on the same chains
+        np.testing.assert_allclose(lp5, lp[:5], rtol=2e-6)
+        np.testing.assert_allclose(gr5, gr[:5], rtol=2e-5, atol=2e-5 * np.abs(gr[:5]).max())
