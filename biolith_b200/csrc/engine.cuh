@@ -139,7 +139,7 @@ constexpr unsigned kHierMinSplits = 64;
 // src[0] + src[stride] + ... (n terms, in index order) with the L2 loads issued 16 at a time: written out because
 // `total += __ldcg(..)` in an unrolled loop is compiled into load -> add -> load (measured with %globaltimer stamps,
 // K1s at C = 8: 74 dependent loads = 21 us of a 107 us evaluation).
-__device__ __forceinline__ double sum_rows(const double* __restrict__ src, size_t stride, unsigned n) {
+static __device__ __noinline__ double sum_rows(const double* __restrict__ src, size_t stride, unsigned n) {
   double total = 0.0;
   for (unsigned b = 0; b < n; b += 16) {
     double v[16];
@@ -151,9 +151,11 @@ __device__ __forceinline__ double sum_rows(const double* __restrict__ src, size_
   return total;
 }
 
+// __noinline__: one copy per translation unit instead of one per kernel instantiation (it runs once per block, and
+// inlining its three reduction paths into ~150 kernels was a third of the library's compile time).
 template <typename T>
-__device__ __forceinline__ void finish_block(const EvalParams& p, int c0, int ncb, int* s_is_last,
-                                             double* coop_scratch = nullptr) {
+__device__ __noinline__ void finish_block(const EvalParams& p, int c0, int ncb, int* s_is_last,
+                                          double* coop_scratch = nullptr) {
   const int tid = threadIdx.x, NQ = p.NQ;
   unsigned int* tickets = p.counters + (size_t)blockIdx.y * kTicketStride;
   const int items = ncb * NQ;

@@ -74,6 +74,24 @@ def test_small_kernel_clamps(ks, ko, J):
     assert_close(lp, gr, ref_lp, ref_gr, 1e-5, "K1s at the clamps")
 
 
+def test_strict_engine_switch(monkeypatch):
+    """BL_STRICT_ENGINE=1 keeps strict math on the libm engine (the A/B reference of the STRICT instantiations)."""
+    import biolith_b200 as bb
+
+    rng = np.random.default_rng(5)
+    X, W, y = _data(rng, 1500, 1, 8, 5, 3)
+    th = rng.uniform(-2, 2, size=(40, 10)).astype(np.float32)
+    with bb.OccupancyLikelihood("occu", X, W, y, strict_math=True) as lk:
+        a = [lk.logp_and_grad(th), lk.logp_and_grad(th[:6])]
+    monkeypatch.setenv("BL_STRICT_ENGINE", "1")
+    with bb.OccupancyLikelihood("occu", X, W, y, strict_math=True) as lk:
+        assert lk.plan(40)["kernel"] == 0 and lk.plan(6)["kernel"] == 0
+        b = [lk.logp_and_grad(th), lk.logp_and_grad(th[:6])]
+    for (lp, gr), (lp0, gr0) in zip(a, b):
+        np.testing.assert_allclose(lp, lp0, rtol=2e-6)
+        np.testing.assert_allclose(gr, gr0, rtol=2e-5, atol=2e-5 * np.abs(gr0).max())
+
+
 def test_small_kernel_matches_engine_and_repeats(monkeypatch):
     """Same numbers (to fp32 rounding) as the site-parallel engine it replaces, bit-identical on repetition, and
     independent of how the chains are batched (a chain's result never depends on its neighbours)."""
@@ -102,8 +120,8 @@ def test_small_kernel_matches_engine_and_repeats(monkeypatch):
 @pytest.mark.parametrize("ks,ko,J", [(5, 3, 8), (2, 2, 5), (8, 4, 13), (1, 1, 3)])
 def test_strict_math_runs_the_chain_kernel_with_libm(ks, ko, J):
     """BL_FLAG_STRICT_MATH (north_star's "fast-math-free expf / log1pf") on occu with >= 32 chains: K1d's STRICT
-    instantiations (libm exp2f / log2f, IEEE division, the engine's libm clamp form in the fallback), not the 4 x
-    slower engine; same 1e-5 bar against the oracle, including thetas at the clamps."""
+    instantiations (libm exp2f / log2f, IEEE division, the engine's libm clamp form in the fallback), not the 3 x
+    slower engine (which still serves strict math below 32 chains); same 1e-5 bar, including thetas at the clamps."""
     import biolith_b200 as bb
     from oracle import occupancy as orc
 
@@ -118,7 +136,7 @@ def test_strict_math_runs_the_chain_kernel_with_libm(ks, ko, J):
     idx = [0, 1, 2, 33, 69]
     ref_lp, ref_gr = orc.logp_grad("occu", th[idx].astype(np.float64), pr)
     with bb.OccupancyLikelihood("occu", X, W, y, strict_math=True) as lk:
-        assert lk.plan(70)["kernel"] == 5 and lk.plan(5)["kernel"] == 0
+        assert lk.plan(70)["kernel"] == 5 and lk.plan(5)["kernel"] == 0  # K1d STRICT / the libm engine
         lp, gr = lk.logp_and_grad(th)
         assert_close(lp[idx], gr[idx], ref_lp, ref_gr, 1e-5, f"strict K1d ks={ks} ko={ko} J={J}")
         lp5, gr5 = lk.logp_and_grad(th[:5])  # the libm engine on the same chains
