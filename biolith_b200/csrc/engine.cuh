@@ -298,7 +298,7 @@ __device__ __forceinline__ void reduce_into(const T* __restrict__ q, bool valid,
 // read-modify-writes per (tile, chain) cost more than the 16-shuffle transposed butterfly they replace and shorten
 // the TMA ring (C = 5: 130 us against 112 us, C = 8: 182 against 154, C = 1 unchanged).
 template <typename T, class Model, int MINB>
-__global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(kBlockThreads, MINB) eval_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   const int F = p.L.F;

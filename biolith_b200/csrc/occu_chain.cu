@@ -131,7 +131,7 @@ __device__ __forceinline__ void chain_tile(const float* __restrict__ tile, const
 }
 
 template <int KS, int KO, int NS, int MINB, int BT, int JT>
-__global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(BT, MINB) occu_chain_kernel(const __grid_constant__ EvalParams p) {
   // accumulator slots: [0] unused, [1 .. KB] beta (KB = KSM + 1 slots, ks + 1 used), then KA alpha slots
   constexpr int KSM = KS < 0 ? kChainMaxKs : KS;
   constexpr int KB = KSM + 1, KA = KO + 1, NQ = 1 + KB + KA;

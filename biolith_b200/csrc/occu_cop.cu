@@ -157,7 +157,7 @@ struct OccuCopModel {
 // rate -> 3 MUFU like the Bernoulli kernel.
 // ------------------------------------------------------------------------------------------------
 template <int KS, int KO, int BT, int JT>
-__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_cop_chain_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_cop_chain_kernel(const __grid_constant__ EvalParams p) {
   // KS < 0: runtime number of site covariates (<= 8); accumulator slots are laid out for the capacity
   constexpr int KSM = KS < 0 ? 8 : KS;
   constexpr int KB = KSM + 1, KA = KO + 1, NS = 4, NQM = 1 + KB + KA + 2;

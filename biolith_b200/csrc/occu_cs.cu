@@ -185,7 +185,7 @@ struct OccuCsModel {
 // KS < 0: runtime number of site covariates (<= 8), accumulator slots laid out for the capacity.
 // ------------------------------------------------------------------------------------------
 template <int KS, int KO, int BT>
-__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_cs_chain_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_cs_chain_kernel(const __grid_constant__ EvalParams p) {
   using N = Num<float>;
   constexpr int KSM = KS < 0 ? 8 : KS;
   constexpr int KB = KSM + 1, KA = KO + 1, NS = 2, NQM = 1 + KB + KA + 4, EX = 1 + KB + KA;

@@ -244,7 +244,7 @@ struct OccuRnModel {
 // RT = true: KS / KO are capacities and the actual covariate counts come from the layout (the k-loops
 // dominate, so the predicated site-level loops cost nothing measurable)
 template <int KS, int KO, int BT, bool RT>
-__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_rn_chain_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(BT, BT == 128 ? 4 : 2) occu_rn_chain_kernel(const __grid_constant__ EvalParams p) {
   using N = Num<float>;
   using M = Mth<float, true>;
   constexpr int KB = KS + 1, KA = KO + 1;

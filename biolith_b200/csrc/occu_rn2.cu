@@ -429,7 +429,7 @@ __device__ __forceinline__ bool rn2_dispatch(int n1, const float* __restrict__ v
 }
 
 template <int KO, int JT, int BT>
-__global__ void __launch_bounds__(BT, BT == 128 ? 3 : 2) occu_rn2_kernel(const EvalParams p, const Rn2Layout S) {
+__global__ void __launch_bounds__(BT, BT == 128 ? 3 : 2) occu_rn2_kernel(const __grid_constant__ EvalParams p, const Rn2Layout S) {
   constexpr int KSM = kRn2MaxKs, KB = KSM + 1, KA = KO + 1, NQ = 1 + KB + KA;
   constexpr int VR = KO + 1 <= 4 ? 4 : 8;
   const int ks = S.ks, XR = S.XR, R = S.R, K = p.K;

@@ -258,7 +258,7 @@ __device__ __forceinline__ void visit_block(const float* __restrict__ vp, const 
 // the block barrier per ring slot (288 threads -> 96..112 registers): 7.76 ms against 7.32 ms; three resident
 // blocks per SM (72..80 registers, spills): 8.2 ms.
 template <int KS, int KO, int NQD, int NS, int MINB, int BT, bool STRICT>
-__global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const EvalParams p, const SignedLayout S) {
+__global__ void __launch_bounds__(BT, MINB) occu_signed_kernel(const __grid_constant__ EvalParams p, const SignedLayout S) {
   using M = SMath<STRICT>;
   constexpr int KSM = KS < 0 ? kSignedMaxKs : KS;
   constexpr int KB = KSM + 1, KA = KO + 1, NQ = 1 + KB + KA;

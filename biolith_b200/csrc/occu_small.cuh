@@ -179,7 +179,7 @@ __device__ __forceinline__ void small_decode(const float* __restrict__ tile, int
 // KS < 0: runtime Ks (<= kSmallMaxKs).  J8: the site's 8 visits are decoded once into registers (J == 8); otherwise
 // visits are decoded per chain from shared memory in quads (any J).
 template <int KS, int KO, bool J8, int NC, bool STRICT>
-__global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const EvalParams p) {
+__global__ void __launch_bounds__(small_bt(NC), 1) occu_small_kernel(const __grid_constant__ EvalParams p) {
   using M = SmMath<STRICT>;
   constexpr int kSmallBT = small_bt(NC), kSmallWarpsMax = kSmallBT / kWarp;
   const int kSmallWarps = (int)blockDim.x / kWarp;  // fewer than the maximum when a warp-tile is wide (ring budget)

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_plan_geometry_invariants(tmp_path):
     exe = tmp_path / "geometry_check"
     src = os.path.join(ROOT, "tests", "cpp", "geometry_check.cu")
-    cc = subprocess.run(["nvcc", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", str(exe), src],
+    cc = subprocess.run(["nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe), src],
                         capture_output=True, text=True, timeout=600)
     assert cc.returncode == 0, cc.stderr[-2000:]
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
