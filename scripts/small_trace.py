@@ -1,4 +1,4 @@
-"""Block timeline of K1s (build with BL_EXTRA_NVCC_FLAGS=-DBL_TRACE): %globaltimer stamps per block, summarised."""
+"""Block timeline of K1s: %globaltimer stamps per block, summarised (needs scripts/build_trace_lib.sh first)."""
 import ctypes, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
