@@ -42,12 +42,30 @@ constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - (float)log2(e):
 constexpr float kLn2Lo = -1.9046542121259336e-09f;  // ln(2)   - (float)ln(2)
 
 // Elementary functions of K1d.  Default: the bounded-error SFU forms (ex2.approx, lg2.approx, rcp.approx + Newton).
-// STRICT (BL_FLAG_STRICT_MATH): libm exp2f / log2f and IEEE division -- north_star's "fast-math-free" clause -- in the
+// STRICT (BL_FLAG_STRICT_MATH): an FMA-pipe exp2 (below), libm log2f and IEEE division -- north_star's "fast-math-free" clause -- in the
 // SAME formulation (one exponential per visit, product-log, batch inversion are algebra, not approximations), so the
 // conformant path costs ~100 instructions per (site, chain) more instead of running the 4 x slower engine.
+// 2^x on the FMA pipe: n = rint(x), 2^(x - n) by its degree-7 Taylor polynomial on [-1/2, 1/2] (truncation 5e-9,
+// seven FMAs: ~1 ulp, and -- unlike MUFU.EX2, which libm's exp2f also ends in -- no systematic error: near the
+// posterior mode a 5e-8 mean relative error of the exponential IS the gradient error, scripts/ex2_bias_emulation.py).
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fminf(fmaxf(x, -126.0f), 126.0f);
+  const float n = rintf(x);
+  const float f = x - n;
+  float p = 1.525273380405984e-05f;
+  p = fmaf(p, f, 1.5403530393381608e-04f);
+  p = fmaf(p, f, 1.3333558146428443e-03f);
+  p = fmaf(p, f, 9.618129107628477e-03f);
+  p = fmaf(p, f, 5.550410866482158e-02f);
+  p = fmaf(p, f, 2.402265069591007e-01f);
+  p = fmaf(p, f, 6.931471805599453e-01f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + ((int)n << 23));  // p in [0.70, 1.42]: the exponent add cannot carry out
+}
+
 template <bool STRICT> struct SMath {
   static __device__ __forceinline__ float ex2(float x) {
-    if constexpr (STRICT) return exp2f(x); else return sfu::ex2(x);
+    if constexpr (STRICT) return exp2_fma(x); else return sfu::ex2(x);
   }
   static __device__ __forceinline__ float lg2(float x) {
     if constexpr (STRICT) return log2f(x); else return sfu::lg2(x);
