@@ -391,7 +391,7 @@ def main():
                     ms_s = min(strict.eval_timed(d_theta.ptr, chains, d_logp.ptr, d_grad.ptr, stream, iters=2)
                                for _ in range(2))
                 line["strict_math"] = {"ms_per_step": ms_s, "value": chains / (ms_s * 1e-3), "unit": UNIT,
-                                       "note": "BL_FLAG_STRICT_MATH: libm exp2f / log2f and IEEE division in the K1d formulation (engine: BL_STRICT_ENGINE=1), same data and thetas"}
+                                       "note": "BL_FLAG_STRICT_MATH: FMA-pipe exp2, libm log2f and IEEE division (no MUFU) in the K1d formulation (engine: BL_STRICT_ENGINE=1), same data and thetas"}
             except Exception as exc:  # noqa: BLE001
                 line["strict_math"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline and world == 1 and model in ("occu", "occu_cop", "occu_rn"):

@@ -120,8 +120,8 @@ def test_small_kernel_matches_engine_and_repeats(monkeypatch):
 @pytest.mark.parametrize("ks,ko,J", [(5, 3, 8), (2, 2, 5), (8, 4, 13), (1, 1, 3)])
 def test_strict_math_runs_the_chain_kernel_with_libm(ks, ko, J):
     """BL_FLAG_STRICT_MATH (north_star's "fast-math-free expf / log1pf") on occu with >= 32 chains: K1d's STRICT
-    instantiations (libm exp2f / log2f, IEEE division, the engine's libm clamp form in the fallback), not the 3 x
-    slower engine (which still serves strict math below 32 chains); same 1e-5 bar, including thetas at the clamps."""
+    instantiations (FMA-pipe exp2, libm log2f, IEEE division, the engine's libm clamp form in the fallback), not the
+    2.2 x slower engine (which still serves strict math below 32 chains); same 1e-5 bar, including thetas at the clamps."""
     import biolith_b200 as bb
     from oracle import occupancy as orc
 
