@@ -41,6 +41,14 @@ constexpr double kLog2eD = 1.4426950408889634074, kLn2D = 0.6931471805599453094;
 constexpr float kLog2eLo = 1.925963033500011e-08f;  // log2(e) - (float)log2(e): second term of the two-float constant
 constexpr float kLn2Lo = -1.9046542121259336e-09f;  // ln(2)   - (float)ln(2)
 
+// MUFU.EX2 on B200 has a mean relative error of -5e-8 for negative arguments (profiles/r02_mufu_error.txt), and near
+// the posterior mode that bias IS most of the gradient error (scripts/ex2_bias_emulation.py).  Shifting the argument by
+// +5e-8 / ln 2 compensates it where it matters; BL_SIGNED_EX2_SHIFT=0 at build time (-DBL_SIGNED_EX2_SHIFT=0) removes it.
+#ifndef BL_SIGNED_EX2_SHIFT
+#define BL_SIGNED_EX2_SHIFT 1
+#endif
+constexpr float kEx2Shift = BL_SIGNED_EX2_SHIFT ? 7.2134752e-08f : 0.0f;
+
 // Elementary functions of K1d.  Default: the bounded-error SFU forms (ex2.approx, lg2.approx, rcp.approx + Newton).
 // STRICT (BL_FLAG_STRICT_MATH): an FMA-pipe exp2 (below), libm log2f and IEEE division -- north_star's "fast-math-free" clause -- in the
 // SAME formulation (one exponential per visit, product-log, batch inversion are algebra, not approximations), so the
@@ -237,7 +245,9 @@ __device__ __forceinline__ void visit_block(const float* __restrict__ vp, const 
   float e[NV], u[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    float x2 = v[j * VR] * a2[KO + 1];  // sgn * A_lo
+    // sgn * A_lo (+ a sub-ulp offset that cancels MUFU.EX2's mean error at the negative arguments that dominate; it
+    // survives the roundings of the chain below statistically, like A_lo itself -- see kEx2Shift)
+    float x2 = STRICT ? v[j * VR] * a2[KO + 1] : fmaf(v[j * VR], a2[KO + 1], kEx2Shift);
 #pragma unroll
     for (int k = 0; k < KO; ++k) x2 = fmaf(v[j * VR + 1 + k], a2[1 + k], x2);
     x2 = fmaf(v[j * VR], a2[0], x2);    // + sgn * A_hi

@@ -36,6 +36,7 @@ constexpr int kSmallMaxKs = 8;
 constexpr int kSmallThetaStride = 16;              // staged theta row: [beta (KBM) | alpha_0, alpha_1..KO], padded
 constexpr float kSmLog2eLo = 1.925963033500011e-08f;  // log2(e) - (float)log2(e)
 constexpr float kSmClampProduct = 8388608.0f;         // 2^23 > (1 - eps) / eps
+constexpr float kSmEx2Shift = 7.2134752e-08f;         // 5e-8 / ln 2
 
 // Elementary functions: bounded-error SFU forms, or (STRICT = BL_FLAG_STRICT_MATH) libm exp2f / log2f and IEEE
 // division in the same formulation -- as K1d's SMath (occu_signed.cu).
@@ -130,7 +131,9 @@ __device__ __forceinline__ void small_visits(const float (&s)[NV], const float (
     float xp = s[j] * al[0];
 #pragma unroll
     for (int k = 0; k < KO; ++k) xp = fmaf(sw[j][k], al[1 + k], xp);
-    e[j] = M::ex2(fmaf(xp, -kSmLog2eLo, xp * -sfu::kLog2e));  // exp(-x')
+    // exp(-x'); the SFU form shifts the argument by +5e-8 / ln 2: MUFU.EX2's mean error at negative arguments,
+    // compensated where it matters (K1d's kEx2Shift, occu_signed.cu; scripts/ex2_bias_emulation.py)
+    e[j] = M::ex2(fmaf(xp, -kSmLog2eLo, STRICT ? xp * -sfu::kLog2e : fmaf(xp, -sfu::kLog2e, kSmEx2Shift)));
     u[j] = 1.0f + e[j];
   }
   float pr[NV / 2], rp[NV / 2];
