@@ -537,9 +537,9 @@ size_t occu_rn2_smem(const Layout& L, int nstage, int K, int bt) {
 
 // threads (= chains) per block.  Measured on B200 (config 3, K = 50, 256 chains, ms per evaluation): 128 threads
 // (167 registers, no spills, 3 blocks / SM) 9.08, 256 threads (128 registers, spills in the wide instantiations) 9.30
+// (the 256-thread instantiations were a tuning switch only; dropped: they doubled this file's compile time)
 int occu_rn2_block_threads(const Layout& L, int C, int K, size_t smem_limit) {
   (void)L; (void)C; (void)K; (void)smem_limit;
-  if (const char* e = getenv("BL_RN2_BT")) return atoi(e) == 256 ? 256 : 128;
   return 128;
 }
 
@@ -578,8 +578,8 @@ static cudaError_t launch_rn2_one(const EvalParams& p, const Rn2Layout& S, dim3 
 template <int KO, int JT>
 static cudaError_t launch_rn2_bt(const EvalParams& p, const Rn2Layout& S, dim3 grid, size_t smem, cudaStream_t st,
                                  int* occ) {
-  if (p.chain_bt == 128) return launch_rn2_one<KO, JT, 128>(p, S, grid, smem, st, occ);
-  return launch_rn2_one<KO, JT, 256>(p, S, grid, smem, st, occ);
+  if (p.chain_bt != 128) return cudaErrorNotSupported;
+  return launch_rn2_one<KO, JT, 128>(p, S, grid, smem, st, occ);
 }
 
 template <int KO>

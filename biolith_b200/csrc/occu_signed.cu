@@ -546,25 +546,16 @@ int occu_signed_block_threads(int C) {
   return (C > 0 && C % 256 == 0) ? 256 : 128;
 }
 
-static int signed_ns() {
-  const char* e = getenv("BL_SIGNED_NS");  // tuning switch, read when a launch is configured
-  return e ? atoi(e) : 0;
-}
-
+// Two sites interleaved per thread (measured, config 2 near the mode, ms: two 7.34, one 7.75; the one-site
+// instantiations were a tuning switch only and are no longer built).
 template <int KS, int KO, int NQD>
 static cudaError_t launch_signed_bt(const EvalParams& p, const SignedLayout& S, dim3 grid, size_t smem,
                                     cudaStream_t st, int* occ) {
-  const int ns = signed_ns();
-  if (p.flags & BL_FLAG_STRICT_MATH) {  // libm exp2f / log2f, IEEE division (the tuning variants are SFU-only)
+  if (p.flags & BL_FLAG_STRICT_MATH) {  // FMA-pipe exp2, libm log2f, IEEE division
     if (p.chain_bt == 128) return launch_signed_one<KS, KO, NQD, 2, 4, 128, true>(p, S, grid, smem, st, occ);
     return launch_signed_one<KS, KO, NQD, 2, 2, 256, true>(p, S, grid, smem, st, occ);
   }
-  if (p.chain_bt == 128) {
-    if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 4, 128>(p, S, grid, smem, st, occ);
-    return launch_signed_one<KS, KO, NQD, 2, 4, 128>(p, S, grid, smem, st, occ);
-  }
-  // measured (config 2 near the mode, ms): two sites interleaved 7.34, one 7.75
-  if (ns == 1) return launch_signed_one<KS, KO, NQD, 1, 2, 256>(p, S, grid, smem, st, occ);
+  if (p.chain_bt == 128) return launch_signed_one<KS, KO, NQD, 2, 4, 128>(p, S, grid, smem, st, occ);
   return launch_signed_one<KS, KO, NQD, 2, 2, 256>(p, S, grid, smem, st, occ);
 }
 
