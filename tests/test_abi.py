@@ -61,3 +61,18 @@ def test_product_does_not_import_oracle_or_torch():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
                 assert not re.search(r"^\s*(from|import)\s+(torch|triton)\b", src, re.M), f"{f} imports torch/triton"
+
+
+def test_argument_validation_needs_no_device():
+    """NULL handles / outputs are rejected before any CUDA call (same status on CPU-only hosts and GPU boxes)."""
+    import ctypes as C
+
+    from biolith_b200 import _lib
+
+    lib = _lib.load()
+    k = C.c_int32(-1)
+    assert lib.bl_plan_kernel(None, 5, C.byref(k), None, None, None) == -1   # BL_ERR_INVALID
+    assert lib.bl_last_error().decode() != ""
+    ms = C.c_float()
+    assert lib.bl_eval_timed(None, None, 1, None, None, None, 1, C.byref(ms)) != 0
+    assert lib.bl_dataset_info(None, None) != 0
